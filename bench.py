@@ -1,0 +1,306 @@
+"""
+bench.py -- converged SSN solves/s on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference C solver on host cores
+
+Workload (BASELINE.json configs[1]): ring SSN with n_sites=201 (2N=402), 1024
+sampled networks x 8 stimuli per GPU and per step; new_JDS parameters,
+asym_tanh, k=0.01, n=2.2, tau=(0.01589, 0.002), dt=8e-4, atol=1e-5, r0=0
+(SURVEY.md section 8d).  z ~ U[0,1) float32 is synthetic (torch Philox on the
+device / numpy on the host); W is built on chip from z.
+
+* value : converged (status 0) solves of all ranks / max-over-ranks device time,
+          inputs resident in HBM (CUDA events on the launching stream).
+* e2e   : same metric through the C ABI with HOST buffers: pinned z in, R/status
+          out, host<->device copies inside the timed region (wall clock around the
+          synchronous call).
+* roofline : FP32 FFMA.  achieved = sum over solves of sweeps x 2 (2N)^2 flops /
+          fixed-point kernel time; peak = FP32 FMA throughput measured in this run
+          by the library's probe kernel (MEASURED_PEAKS.json carries only HBM and
+          bf16 numbers; its HBM figure is reported beside for the secondary bound).
+* cpu_baseline / --impl reference : the UNMODIFIED reference C solver
+          (oracle/_ref/libssnode.so) driven by a thread pool as
+          tc_gan.ssnode.find_fixed_points_parallel does, on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SITES, NZ, NB_BANDWIDTHS = 201, 1024, [0, 0.0625, 0.125, 0.1875, 0.25, 0.5, 0.75, 1]
+METRIC = 'converged SSN solves/sec (2N=402, 8 stim)'
+UNIT = 'solves/s'
+
+
+def workload_config(nz):
+    return {'workload': 'configs[1]: ssnode fixed-point solve, n_sites=201 (2N=402), %d networks x 8 stimuli per GPU per step' % nz,
+            'io_type': 'asym_tanh', 'params': 'new_JDS', 'dt': 8e-4, 'atol': 1e-5, 'max_iter': 10000,
+            'networks_per_gpu': nz, 'stimuli': 8, 'l2': 'inputs larger than L2 (z = %.0f MB per step)' % (nz * 402 * 402 * 4 / 1e6)}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation on the host cores (rank 0 only)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import numpy as np
+    import ssn_oracle as so
+    cores = int(os.environ.get('OMP_NUM_THREADS', 0)) or (os.cpu_count() or 1)
+    kind = 'reference' if so.ref_lib() is not None else 'port'
+    nz = max(8, min(64, 2 * cores))            # bounded sample of the 1024-network step
+    jds = so.new_JDS()
+    exts = so.stimulus_input(so.DEFAULT_BANDWIDTHS, N_SITES)
+    rs = np.random.RandomState(0)
+    z = rs.rand(nz, 2 * N_SITES, 2 * N_SITES).astype(np.float32).astype(np.float64)
+    W = so.generate_weight(N_SITES, jds['J'], jds['D'], jds['S'], z)
+
+    def step():
+        if kind == 'reference':
+            _, st = so.ref_fixed_point_batch(W, exts, threads=cores)
+        else:
+            _, st, _ = so.fixed_point_batch(W, exts, threads=cores, stop_at_first_failure=True)
+        return int((st == 0).sum())
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.time()
+    solved = sum(step() for _ in range(args.steps))
+    dt = time.time() - t0
+    value = solved / dt
+    sample = '%d of %d networks x 8 stimuli per step, %d steps' % (nz, NZ, args.steps)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(NZ),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}))
+
+
+def cpu_baseline(seconds_budget=20.0):
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import numpy as np
+    import ssn_oracle as so
+    cores = int(os.environ.get('OMP_NUM_THREADS', 0)) or (os.cpu_count() or 1)
+    kind = 'reference' if so.ref_lib() is not None else 'port'
+    nz = max(8, min(64, 2 * cores))
+    jds = so.new_JDS()
+    exts = so.stimulus_input(so.DEFAULT_BANDWIDTHS, N_SITES)
+    z = np.random.RandomState(0).rand(nz, 2 * N_SITES, 2 * N_SITES).astype(np.float32).astype(np.float64)
+    W = so.generate_weight(N_SITES, jds['J'], jds['D'], jds['S'], z)
+    t0 = time.time()
+    if kind == 'reference':
+        _, st = so.ref_fixed_point_batch(W, exts, threads=cores)
+    else:
+        _, st, _ = so.fixed_point_batch(W, exts, threads=cores, stop_at_first_failure=True)
+    dt = time.time() - t0
+    return {'value': float((st == 0).sum() / dt), 'unit': UNIT, 'cores': cores, 'kind': kind,
+            'sample': '%d of %d networks x 8 stimuli, one pass (%.1f s)' % (nz, NZ, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--networks', type=int, default=NZ, help='networks per GPU per step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tc_gan_b200 import clib, ssnode, stimuli
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if clib.libssnode.ssn_device_count() < 1:
+        raise SystemExit('bench.py: no CUDA device; the SSN library has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    nz, n_sites, dim = args.networks, N_SITES, 2 * N_SITES
+    P = ssnode.DEFAULT_PARAMS
+    jds = ssnode.new_JDS()
+    exts_np = stimuli.input(NB_BANDWIDTHS, np.linspace(-.5, .5, n_sites), P['smoothness'], P['contrast'])
+    nb = len(exts_np)
+    sv = clib.make_solver(k=P['k'], n=P['n'])
+    jd = clib.make_jds(jds['J'], jds['D'], jds['S'])
+    lib = clib.libssnode
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)             # networks are sharded: every rank owns different z
+    z = torch.rand((nz, dim, dim), generator=gen, device=dev, dtype=torch.float32)
+    ext = torch.tensor(exts_np, dtype=torch.float32, device=dev)
+    R = torch.empty((nz, nb, dim), dtype=torch.float32, device=dev)
+    status = torch.empty((nz, nb), dtype=torch.int32, device=dev)
+    iters = torch.empty((nz, nb), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        clib.check_call(lib.ssn_fixed_point_batch(
+            sv, nz, nb, n_sites, clib.W_FROM_Z, z.data_ptr(), jd, ext.data_ptr(), 0, None,
+            R.data_ptr(), status.data_ptr(), iters.data_ptr(), 0, clib.MEM_DEVICE, stream.cuda_stream),
+            'ssn_fixed_point_batch')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = clib.kernel_launches()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.time()
+    ev[0].record(stream)
+    for s in range(args.steps):
+        step_device()
+        ev[s + 1].record(stream)
+    barrier()
+    t_wall1 = time.time()
+    launches = clib.kernel_launches() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    dev_ms = ev[0].elapsed_time(ev[-1])
+    converged = int((status == 0).sum().item())
+    sweeps = int(iters.to(torch.int64).sum().item())       # same inputs every step -> same counts
+
+    # ---- end to end: host buffers through the C ABI --------------------------------------
+    z_host = torch.empty((nz, dim, dim), dtype=torch.float32, pin_memory=True)
+    z_host.copy_(z)
+    ext_host = np.ascontiguousarray(exts_np, np.float32)
+    R_host = torch.empty((nz, nb, dim), dtype=torch.float32, pin_memory=True)
+    st_host = torch.empty((nz, nb), dtype=torch.int32, pin_memory=True)
+    it_host = torch.empty((nz, nb), dtype=torch.int32, pin_memory=True)
+
+    def step_host():
+        clib.check_call(lib.ssn_fixed_point_batch(
+            sv, nz, nb, n_sites, clib.W_FROM_Z, z_host.data_ptr(), jd, ext_host.ctypes.data, 0, None,
+            R_host.data_ptr(), st_host.data_ptr(), it_host.data_ptr(), 0, clib.MEM_HOST, None),
+            'ssn_fixed_point_batch(host)')
+        return int((st_host == 0).sum().item())
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_host()
+    barrier()
+    t0 = time.time()
+    e2e_conv = sum(step_host() for _ in range(e2e_steps))
+    e2e_s = time.time() - t0
+    h2d = z_host.numel() * 4 + ext_host.nbytes
+    d2h = R_host.numel() * 4 + st_host.numel() * 4 + it_host.numel() * 4
+
+    # ---- reduce over ranks (max time, summed work) -------------------------------------------
+    stats = torch.tensor([dev_ms, e2e_s, float(converged), float(e2e_conv), float(sweeps)],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = stats.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = stats.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s = tmax[0].item(), tmax[1].item()
+        conv_all, e2e_conv_all, sweeps_all = tsum[2].item(), tsum[3].item(), tsum[4].item()
+    else:
+        conv_all, e2e_conv_all, sweeps_all = float(converged), float(e2e_conv), float(sweeps)
+
+    if rank == 0:
+        value = conv_all * args.steps / (dev_ms * 1e-3)
+        flops_per_step = sweeps * 2.0 * dim * dim          # rank 0's kernel: reference-equivalent sweeps
+        # the fixed-point kernel is >99% of a step (memset + status fix-up are the other launches)
+        kernel_ms = dev_ms / args.steps
+        achieved = flops_per_step / (kernel_ms * 1e-3) * 1e-12
+        peak = ctypes.c_double(0.0)
+        clib.check_call(lib.ssn_measure_fp32_peak(ctypes.byref(peak)), 'ssn_measure_fp32_peak')
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except (OSError, ValueError):
+            pass
+        algo_bytes = nz * (dim * dim * 4 + nb * dim * 4 + nb * 8) + nb * dim * 4
+        cs, rc = ctypes.c_int(0), ctypes.c_int(0)
+        lib.ssn_fixed_point_occupancy(n_sites, ctypes.byref(cs), ctypes.byref(rc))
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 contraction / f64 state', 'data': 'synthetic',
+            'config': dict(workload_config(nz), cluster_size=cs.value, resident_clusters=rc.value,
+                           mean_sweeps_per_solve=sweeps / float(nz * nb)),
+            'clocks': clocks,
+            'e2e': {'value': e2e_conv_all / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'steps': e2e_steps},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'fp32_ffma', 'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
+                         'frac': achieved / peak.value if peak.value else None, 'traffic': None,
+                         'peak_source': 'measured in this run (ssn_measure_fp32_peak); nominal 148 SM x 128 FMA x 2 x clock',
+                         'hbm': {'achieved_gbs': algo_bytes / (kernel_ms * 1e-3) * 1e-9,
+                                 'peak_gbs': peaks.get('hbm_gbs', 6650.0),
+                                 'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback'}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

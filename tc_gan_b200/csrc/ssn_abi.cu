@@ -1,0 +1,483 @@
+// extern "C" surface of libssnode.so (see include/ssnode.h): the reference ABI
+// symbols of tc_gan/ext/ssnode.c plus the batched entry points, host staging and
+// per-thread CUDA state.  No CPU fallback anywhere: without a usable GPU every
+// solver call returns 1000 + cudaError_t and ssn_last_error() says why.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "ssn_launch.h"
+
+namespace ssn {
+
+// ---- error text, launch counter ------------------------------------------------
+static thread_local char tl_error[512] = "";
+static std::atomic<int> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return 1000 + (int)e;
+}
+
+// ---- work-counter ring for device-pointer calls (one int per launch) ------------
+static std::mutex g_counter_mutex;
+static int *g_counters[64] = {nullptr};
+static int g_counter_pos[64] = {0};
+constexpr int COUNTER_RING = 256;
+
+static int next_counter(int **out) {
+    int dev = 0;
+    SSN_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_counter_mutex);
+    if (!g_counters[dev]) SSN_CUDA(cudaMalloc(&g_counters[dev], COUNTER_RING * sizeof(int)));
+    *out = g_counters[dev] + (g_counter_pos[dev]++ % COUNTER_RING);
+    return 0;
+}
+
+// ---- per-thread host staging ------------------------------------------------------
+struct HostCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> slot;
+    std::vector<size_t> cap;
+    int ensure_device() {
+        int dev = 0;
+        SSN_CUDA(cudaGetDevice(&dev));
+        if (dev != device) {
+            release();
+            device = dev;
+            SSN_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        }
+        return 0;
+    }
+    int get(int i, size_t bytes, void **out) {
+        if ((int)slot.size() <= i) { slot.resize(i + 1, nullptr); cap.resize(i + 1, 0); }
+        if (cap[i] < bytes) {
+            if (slot[i]) cudaFree(slot[i]);
+            slot[i] = nullptr; cap[i] = 0;
+            SSN_CUDA(cudaMalloc(&slot[i], bytes));
+            cap[i] = bytes;
+        }
+        *out = slot[i];
+        return 0;
+    }
+    void release() {
+        for (void *p : slot) if (p) cudaFree(p);
+        slot.clear(); cap.clear();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+    ~HostCtx() { release(); }
+};
+static thread_local HostCtx tl_ctx;
+
+#define GET(i, T, n, var) T *var = nullptr; { void *_p; int _rc = tl_ctx.get(i, (size_t)(n) * sizeof(T), &_p); if (_rc) return _rc; var = (T *)_p; }
+
+// ---- small conversion / weight kernels --------------------------------------------
+__global__ void convert_f64_f32_kernel(const double *s, float *d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = (float)s[i];
+}
+__global__ void convert_f32_f64_kernel(const float *s, double *d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = (double)s[i];
+}
+static int grid_for(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
+int launch_convert_f64_to_f32(const double *s, float *d, size_t n, cudaStream_t st) {
+    if (!n) return 0;
+    convert_f64_f32_kernel<<<grid_for(n), 256, 0, st>>>(s, d, n);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "convert_f64_f32");
+}
+int launch_convert_f32_to_f64(const float *s, double *d, size_t n, cudaStream_t st) {
+    if (!n) return 0;
+    convert_f32_f64_kernel<<<grid_for(n), 256, 0, st>>>(s, d, n);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "convert_f32_f64");
+}
+
+__global__ void generate_weight_kernel(int n_sites, const float *z, WeightConst wc, float *W, size_t total) {
+    const int dim = 2 * n_sites;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e % dim), i = (int)((e / dim) % dim);
+        const int a = i >= n_sites, b = j >= n_sites, ab = a * 2 + b;
+        const float d = (float)((i - a * n_sites) - (j - b * n_sites)) * wc.dx;
+        W[e] = expf(-d * d * wc.inv2s2[ab]) * fmaf(wc.sD[ab], z[e], wc.sJ[ab]);
+    }
+}
+int launch_generate_weight(int nz, int n_sites, const float *z, const ssn_jds &jds, float *W, cudaStream_t st) {
+    const size_t total = (size_t)nz * 4 * n_sites * n_sites;
+    if (!total) return 0;
+    generate_weight_kernel<<<grid_for(total), 256, 0, st>>>(n_sites, z, make_weight_const(jds, n_sites), W, total);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "generate_weight");
+}
+
+// FP32 FFMA peak probe: 8 independent FMA chains per thread, 1024 threads per SM-sized block.
+__global__ void __launch_bounds__(1024) ffma_peak_kernel(float *out, int iters, float a, float b) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 12345.678f) out[0] = s;          // never true; keeps the chains alive
+}
+
+static int validate(const ssn_solver *sv, int nz, int nb, int n_sites) {
+    if (!sv) { set_error("solver is NULL"); return -1; }
+    if (sv->io_type < 0 || sv->io_type > 2) { set_error("unknown io_type %d", sv->io_type); return -1; }
+    if (nz < 0 || nb < 0 || n_sites < 1) { set_error("bad shape nz=%d nb=%d n_sites=%d", nz, nb, n_sites); return -1; }
+    return 0;
+}
+
+// ---- reference ABI: one network x one stimulus, float64 ----------------------------
+static int legacy_solve(int io_type, int N, double *W, double *ext, double k, double n, double *r0, double *r1,
+                        double tau_E, double tau_I, double dt, int max_iter, double atol,
+                        double rate_soft_bound, double rate_hard_bound) {
+    if (N < 1) { set_error("N must be positive"); return 1000; }
+    int rc = tl_ctx.ensure_device();
+    if (rc) return rc;
+    const size_t dim = 2 * (size_t)N;
+    cudaStream_t st = tl_ctx.stream;
+    GET(0, double, dim * dim, dW);
+    GET(1, double, dim, dE);
+    GET(2, double, dim, dR0);
+    GET(3, double, dim, dR);
+    GET(4, int, 2, dS);
+    SSN_CUDA(cudaMemcpyAsync(dW, W, dim * dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    SSN_CUDA(cudaMemcpyAsync(dE, ext, dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    SSN_CUDA(cudaMemcpyAsync(dR0, r0, dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    ssn_solver sv = {};
+    sv.io_type = io_type; sv.max_iter = max_iter; sv.k = k; sv.n = n;
+    sv.tau_E = tau_E; sv.tau_I = tau_I; sv.dt = dt; sv.atol = atol;
+    sv.rate_soft_bound = rate_soft_bound; sv.rate_hard_bound = rate_hard_bound;
+    rc = launch_fixed_point_f64(sv, 1, 1, N, dW, dE, 0, dR0, dR, dS, dS + 1, /*nonfinite_fixup=*/false, st);
+    if (rc) return rc < 0 ? 1000 : rc;
+    int status[2] = {1, 0};
+    SSN_CUDA(cudaMemcpyAsync(r0, dR, dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SSN_CUDA(cudaMemcpyAsync(status, dS, sizeof(status), cudaMemcpyDeviceToHost, st));
+    SSN_CUDA(cudaStreamSynchronize(st));
+    if (r1) memcpy(r1, r0, dim * sizeof(double));
+    return status[0];
+}
+
+}  // namespace ssn
+
+using namespace ssn;
+
+extern "C" {
+
+int solve_dynamics_asym_power_euler(int N, double *W, double *ext, double k, double n, double *r0, double *r1,
+                                    double tau_E, double tau_I, double dt, int max_iter, double atol,
+                                    double rate_soft_bound, double rate_hard_bound) {
+    return legacy_solve(SSN_IO_POWER, N, W, ext, k, n, r0, r1, tau_E, tau_I, dt, max_iter, atol,
+                        rate_soft_bound, rate_hard_bound);
+}
+int solve_dynamics_asym_linear_euler(int N, double *W, double *ext, double k, double n, double *r0, double *r1,
+                                     double tau_E, double tau_I, double dt, int max_iter, double atol,
+                                     double rate_soft_bound, double rate_hard_bound) {
+    return legacy_solve(SSN_IO_LINEAR, N, W, ext, k, n, r0, r1, tau_E, tau_I, dt, max_iter, atol,
+                        rate_soft_bound, rate_hard_bound);
+}
+int solve_dynamics_asym_tanh_euler(int N, double *W, double *ext, double k, double n, double *r0, double *r1,
+                                   double tau_E, double tau_I, double dt, int max_iter, double atol,
+                                   double rate_soft_bound, double rate_hard_bound) {
+    return legacy_solve(SSN_IO_TANH, N, W, ext, k, n, r0, r1, tau_E, tau_I, dt, max_iter, atol,
+                        rate_soft_bound, rate_hard_bound);
+}
+
+// Scalar helpers: the host instantiation of the functions the kernels use.
+double dot(int dim, const double *x, const double *y) {
+    double s = 0.0;
+    for (int i = 0; i < dim; ++i) s += x[i] * y[i];
+    return s;
+}
+double rate_to_volt(double rate, double k, double n) { return pow(rate / k, 1.0 / n); }
+static IoConst<double> scalar_io(int io_type, double r0, double r1, double v0, double k, double n) {
+    IoConst<double> c = make_io_const<double>(io_type, k, n, r0, r1);
+    c.v0 = v0;                                   // the caller's v0 wins, as in the reference signature
+    c.lin_slope = k * pow(v0, n - 1.0) * n;
+    c.tanh_scale = n * r0 / ((r1 - r0) * v0);
+    return c;
+}
+double io_pow(double v, double r0, double r1, double v0, double k, double n) {
+    return io_eval<double>(scalar_io(SSN_IO_POWER, r0, r1, v0, k, n), v);
+}
+double io_alin(double v, double r0, double r1, double v0, double k, double n) {
+    return io_eval<double>(scalar_io(SSN_IO_LINEAR, r0, r1, v0, k, n), v);
+}
+double io_atanh(double v, double r0, double r1, double v0, double k, double n) {
+    return io_eval<double>(scalar_io(SSN_IO_TANH, r0, r1, v0, k, n), v);
+}
+
+// ---- batched fixed points -----------------------------------------------------------
+int ssn_fixed_point_batch(const ssn_solver *solver, int nz, int nb, int n_sites, int w_kind, const float *w,
+                          const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
+                          float *R, int *status, int *iters, int precise, int mem, void *stream) {
+    int rc = validate(solver, nz, nb, n_sites);
+    if (rc) return rc;
+    if (nz == 0 || nb == 0) return 0;
+    const size_t dim = 2 * (size_t)n_sites;
+    if (mem == SSN_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)stream;
+        int *counter = nullptr;
+        if ((rc = next_counter(&counter))) return rc;
+        if (!precise)
+            return launch_fixed_point_f32(*solver, nz, nb, n_sites, w_kind, w, jds, ext, ext_per_network, r_init,
+                                          R, status, iters, counter, st);
+        // float64 kernel on float32 device data: widen into scratch owned by this thread.
+        if ((rc = tl_ctx.ensure_device())) return rc;
+        GET(0, double, (size_t)nz * dim * dim, dW);
+        GET(1, double, (size_t)(ext_per_network ? nz : 1) * nb * dim, dE);
+        GET(2, double, (size_t)nz * nb * dim, dR0);
+        GET(3, double, (size_t)nz * nb * dim, dR);
+        GET(5, float, (size_t)nz * dim * dim, dWf);
+        const float *wsrc = w;
+        if (w_kind == SSN_W_FROM_Z) {
+            if (!jds) { set_error("SSN_W_FROM_Z needs jds"); return -1; }
+            if ((rc = launch_generate_weight(nz, n_sites, w, *jds, dWf, st))) return rc;
+            wsrc = dWf;
+        }
+        if ((rc = launch_convert_f32_to_f64(wsrc, dW, (size_t)nz * dim * dim, st))) return rc;
+        if ((rc = launch_convert_f32_to_f64(ext, dE, (size_t)(ext_per_network ? nz : 1) * nb * dim, st))) return rc;
+        if (r_init && (rc = launch_convert_f32_to_f64(r_init, dR0, (size_t)nz * nb * dim, st))) return rc;
+        if ((rc = launch_fixed_point_f64(*solver, nz, nb, n_sites, dW, dE, ext_per_network, r_init ? dR0 : nullptr,
+                                         dR, status, iters, true, st))) return rc;
+        if ((rc = launch_convert_f64_to_f32(dR, R, (size_t)nz * nb * dim, st))) return rc;
+        // scratch is reused by the next call of this thread: make the stream order explicit
+        return check_cuda(cudaStreamSynchronize(st), "precise device path");
+    }
+
+    // host arrays: stage through this thread's buffers in slabs of networks
+    if ((rc = tl_ctx.ensure_device())) return rc;
+    cudaStream_t st = tl_ctx.stream;
+    const int slab = std::min(nz, 2048);
+    const size_t n_ext = (size_t)(ext_per_network ? slab : 1) * nb * dim;
+    GET(8, float, (size_t)slab * dim * dim, dw);
+    GET(9, float, n_ext, de);
+    GET(10, float, (size_t)slab * nb * dim, dr0);
+    GET(11, float, (size_t)slab * nb * dim, dr);
+    GET(12, int, (size_t)slab * nb * 2, ds);
+    if (!ext_per_network) SSN_CUDA(cudaMemcpyAsync(de, ext, n_ext * sizeof(float), cudaMemcpyHostToDevice, st));
+    for (int z0 = 0; z0 < nz; z0 += slab) {
+        const int m = std::min(slab, nz - z0);
+        SSN_CUDA(cudaMemcpyAsync(dw, w + (size_t)z0 * dim * dim, (size_t)m * dim * dim * sizeof(float),
+                                 cudaMemcpyHostToDevice, st));
+        if (ext_per_network)
+            SSN_CUDA(cudaMemcpyAsync(de, ext + (size_t)z0 * nb * dim, (size_t)m * nb * dim * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+        if (r_init)
+            SSN_CUDA(cudaMemcpyAsync(dr0, r_init + (size_t)z0 * nb * dim, (size_t)m * nb * dim * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+        rc = ssn_fixed_point_batch(solver, m, nb, n_sites, w_kind, dw, jds, de, ext_per_network,
+                                   r_init ? dr0 : nullptr, dr, ds, ds + (size_t)slab * nb, precise,
+                                   SSN_MEM_DEVICE, st);
+        if (rc) return rc;
+        SSN_CUDA(cudaMemcpyAsync(R + (size_t)z0 * nb * dim, dr, (size_t)m * nb * dim * sizeof(float),
+                                 cudaMemcpyDeviceToHost, st));
+        SSN_CUDA(cudaMemcpyAsync(status + (size_t)z0 * nb, ds, (size_t)m * nb * sizeof(int),
+                                 cudaMemcpyDeviceToHost, st));
+        if (iters)
+            SSN_CUDA(cudaMemcpyAsync(iters + (size_t)z0 * nb, ds + (size_t)slab * nb, (size_t)m * nb * sizeof(int),
+                                     cudaMemcpyDeviceToHost, st));
+        SSN_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int ssn_fixed_point_batch_f64(const ssn_solver *solver, int nz, int nb, int n_sites, const double *W,
+                              const double *ext, const double *r_init, double *R, int *status, int *iters,
+                              int precise) {
+    int rc = validate(solver, nz, nb, n_sites);
+    if (rc) return rc;
+    if (nz == 0 || nb == 0) return 0;
+    if ((rc = tl_ctx.ensure_device())) return rc;
+    cudaStream_t st = tl_ctx.stream;
+    const size_t dim = 2 * (size_t)n_sites;
+    const int slab = std::min(nz, 256);
+    GET(0, double, (size_t)slab * dim * dim, dW);
+    GET(1, double, (size_t)nb * dim, dE);
+    GET(2, double, (size_t)slab * nb * dim, dR0);
+    GET(3, double, (size_t)slab * nb * dim, dR);
+    GET(4, int, (size_t)slab * nb * 2, dS);
+    GET(5, float, (size_t)slab * dim * dim, fW);
+    GET(6, float, (size_t)nb * dim, fE);
+    GET(7, float, (size_t)slab * nb * dim * 2, fR);
+    SSN_CUDA(cudaMemcpyAsync(dE, ext, (size_t)nb * dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!precise && (rc = launch_convert_f64_to_f32(dE, fE, (size_t)nb * dim, st))) return rc;
+    int *counter = nullptr;
+    for (int z0 = 0; z0 < nz; z0 += slab) {
+        const int m = std::min(slab, nz - z0);
+        const size_t nR = (size_t)m * nb * dim;
+        SSN_CUDA(cudaMemcpyAsync(dW, W + (size_t)z0 * dim * dim, (size_t)m * dim * dim * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+        if (r_init)
+            SSN_CUDA(cudaMemcpyAsync(dR0, r_init + (size_t)z0 * nb * dim, nR * sizeof(double),
+                                     cudaMemcpyHostToDevice, st));
+        if (precise) {
+            rc = launch_fixed_point_f64(*solver, m, nb, n_sites, dW, dE, 0, r_init ? dR0 : nullptr, dR, dS,
+                                        dS + (size_t)slab * nb, true, st);
+            if (rc) return rc;
+        } else {
+            float *fR0 = fR + (size_t)slab * nb * dim;
+            if ((rc = launch_convert_f64_to_f32(dW, fW, (size_t)m * dim * dim, st))) return rc;
+            if (r_init && (rc = launch_convert_f64_to_f32(dR0, fR0, nR, st))) return rc;
+            if ((rc = next_counter(&counter))) return rc;
+            rc = launch_fixed_point_f32(*solver, m, nb, n_sites, SSN_W_DENSE, fW, nullptr, fE, 0,
+                                        r_init ? fR0 : nullptr, fR, dS, dS + (size_t)slab * nb, counter, st);
+            if (rc) return rc;
+            if ((rc = launch_convert_f32_to_f64(fR, dR, nR, st))) return rc;
+        }
+        SSN_CUDA(cudaMemcpyAsync(R + (size_t)z0 * nb * dim, dR, nR * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SSN_CUDA(cudaMemcpyAsync(status + (size_t)z0 * nb, dS, (size_t)m * nb * sizeof(int),
+                                 cudaMemcpyDeviceToHost, st));
+        if (iters)
+            SSN_CUDA(cudaMemcpyAsync(iters + (size_t)z0 * nb, dS + (size_t)slab * nb, (size_t)m * nb * sizeof(int),
+                                     cudaMemcpyDeviceToHost, st));
+        SSN_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int ssn_generate_weight(int nz, int n_sites, const float *z, const ssn_jds *jds, float *W, int mem, void *stream) {
+    if (!jds || nz < 0 || n_sites < 1) { set_error("bad arguments"); return -1; }
+    if (mem == SSN_MEM_DEVICE) return launch_generate_weight(nz, n_sites, z, *jds, W, (cudaStream_t)stream);
+    int rc = tl_ctx.ensure_device();
+    if (rc) return rc;
+    const size_t total = (size_t)nz * 4 * n_sites * n_sites;
+    GET(8, float, total, dz);
+    GET(5, float, total, dW);
+    cudaStream_t st = tl_ctx.stream;
+    SSN_CUDA(cudaMemcpyAsync(dz, z, total * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = launch_generate_weight(nz, n_sites, dz, *jds, dW, st))) return rc;
+    SSN_CUDA(cudaMemcpyAsync(W, dW, total * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return check_cuda(cudaStreamSynchronize(st), "generate_weight");
+}
+
+// ---- gradients ------------------------------------------------------------------------
+int ssn_ift_gradient_batch(const ssn_solver *solver, int nz, int nb, int n_sites, const float *z,
+                           const ssn_jds *jds, const float *ext, int ext_per_network, const float *R,
+                           const float *g, double rtol, double *grad, float *mu, int *status, int *iters,
+                           int mem, void *stream) {
+    int rc = validate(solver, nz, nb, n_sites);
+    if (rc) return rc;
+    if (!jds) { set_error("jds is NULL"); return -1; }
+    const size_t dim = 2 * (size_t)n_sites;
+    int *counter = nullptr;
+    if ((rc = next_counter(&counter))) return rc;
+    if (mem == SSN_MEM_DEVICE)
+        return launch_ift_gradient(*solver, nz, nb, n_sites, z, *jds, ext, ext_per_network, R, g, rtol, grad, mu,
+                                   status, iters, counter, (cudaStream_t)stream);
+    if ((rc = tl_ctx.ensure_device())) return rc;
+    cudaStream_t st = tl_ctx.stream;
+    const size_t nR = (size_t)nz * nb * dim, nE = (size_t)(ext_per_network ? nz : 1) * nb * dim;
+    GET(8, float, (size_t)nz * dim * dim, dz);
+    GET(9, float, nE, de);
+    GET(10, float, nR, dr);
+    GET(11, float, nR, dg);
+    GET(12, int, (size_t)nz * nb * 2, ds);
+    GET(13, float, nR, dmu);
+    GET(14, double, 12, dgrad);
+    SSN_CUDA(cudaMemcpyAsync(dz, z, (size_t)nz * dim * dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    SSN_CUDA(cudaMemcpyAsync(de, ext, nE * sizeof(float), cudaMemcpyHostToDevice, st));
+    SSN_CUDA(cudaMemcpyAsync(dr, R, nR * sizeof(float), cudaMemcpyHostToDevice, st));
+    SSN_CUDA(cudaMemcpyAsync(dg, g, nR * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = launch_ift_gradient(*solver, nz, nb, n_sites, dz, *jds, de, ext_per_network, dr, dg, rtol, dgrad, dmu, ds,
+                             ds + (size_t)nz * nb, counter, st);
+    if (rc) return rc;
+    SSN_CUDA(cudaMemcpyAsync(grad, dgrad, 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mu) SSN_CUDA(cudaMemcpyAsync(mu, dmu, nR * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (status) SSN_CUDA(cudaMemcpyAsync(status, ds, (size_t)nz * nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters)
+        SSN_CUDA(cudaMemcpyAsync(iters, ds + (size_t)nz * nb, (size_t)nz * nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return check_cuda(cudaStreamSynchronize(st), "ift gradient");
+}
+
+int ssn_euler_forward(const ssn_solver *solver, int nz, int nb, int n_sites, const float *z, const ssn_jds *jds,
+                      const float *ext, int ext_per_network, int seqlen, int skip_steps,
+                      double rate_penalty_threshold, float *time_avg, double *penalties, float *traj, float *gain,
+                      void *stream) {
+    int rc = validate(solver, nz, nb, n_sites);
+    if (rc) return rc;
+    if (!jds || seqlen < 1 || skip_steps < 0 || skip_steps >= seqlen) {
+        set_error("bad euler arguments (seqlen=%d skip_steps=%d)", seqlen, skip_steps);
+        return -1;
+    }
+    int *counter = nullptr;
+    if ((rc = next_counter(&counter))) return rc;
+    return launch_euler_forward(*solver, nz, nb, n_sites, z, *jds, ext, ext_per_network, seqlen, skip_steps,
+                                rate_penalty_threshold, time_avg, penalties, traj, gain, counter,
+                                (cudaStream_t)stream);
+}
+
+int ssn_euler_backward(const ssn_solver *solver, int nz, int nb, int n_sites, const float *z, const ssn_jds *jds,
+                       int seqlen, int skip_steps, double rate_penalty_threshold, const float *grad_time_avg,
+                       double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
+                       double *grad, void *stream) {
+    int rc = validate(solver, nz, nb, n_sites);
+    if (rc) return rc;
+    if (!jds || !traj || !gain || !adj) { set_error("euler backward needs jds, traj, gain, adj"); return -1; }
+    int *counter = nullptr;
+    if ((rc = next_counter(&counter))) return rc;
+    return launch_euler_backward(*solver, nz, nb, n_sites, z, *jds, seqlen, skip_steps, rate_penalty_threshold,
+                                 grad_time_avg, w_dyn, w_rate, traj, gain, adj, grad, counter,
+                                 (cudaStream_t)stream);
+}
+
+// ---- introspection ----------------------------------------------------------------------
+int ssn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+const char *ssn_last_error(void) { return tl_error; }
+int ssn_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+int ssn_fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters) {
+    return fixed_point_occupancy(n_sites, cluster_size, resident_clusters);
+}
+int ssn_measure_fp32_peak(double *tflops) {
+    int dev = 0, sms = 0;
+    SSN_CUDA(cudaGetDevice(&dev));
+    SSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float *d = nullptr;
+    SSN_CUDA(cudaMalloc(&d, sizeof(float)));
+    cudaEvent_t e0, e1;
+    SSN_CUDA(cudaEventCreate(&e0));
+    SSN_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = sms * 2;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        SSN_CUDA(cudaEventRecord(e0, 0));
+        ffma_peak_kernel<<<blocks, 1024>>>(d, iters, 0.999f, 1e-4f);
+        SSN_CUDA(cudaEventRecord(e1, 0));
+        SSN_CUDA(cudaEventSynchronize(e1));
+        count_launch();
+        float ms = 0.f;
+        SSN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * 1024.0 * blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (tflops) *tflops = best;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// Building blocks shared by the cluster-resident SSN kernels (sm_100a).
+//
+// One thread-block cluster owns one network.  CTA `rank` of a cluster of `csize`
+// CTAs keeps rows [rank*rpc, rank*rpc+rpc) of the 2N x 2N matrix (W, or W^T for
+// the adjoint kernels) in its shared memory for the whole life of the network,
+// and the full state panel X[2N][8] (8 stimuli wide) in a double-buffered,
+// bank-conflict-free float4 layout that every CTA of the cluster updates through
+// distributed shared memory once per sweep.
+//
+// Thread mapping inside a CTA: thread = (row group g, k-lane kl), lane = g_in_warp*KL + kl.
+// A thread accumulates a TI x 8 register tile over the columns j = 4*(s*KL+kl)+q,
+// q = 0..3, s = 0..kpad/(4 KL)-1:  one LDS.128 of W per row per step (the 8 lanes
+// of a quarter warp read 128 contiguous bytes), and two broadcast LDS.128 of X
+// per column (all row groups of a warp read the same address).  The KL partial
+// tiles are then reduce-scattered with warp shuffles so that lane kl ends up
+// with the TI finished sums of stimulus kl.
+#pragma once
+#include <cooperative_groups.h>
+#include "ssn_common.cuh"
+
+namespace ssn {
+namespace cg = cooperative_groups;
+
+constexpr int TB = 8;          // stimuli per panel
+constexpr int MAX_CLUSTER = 8;
+
+// Panel layout: plane h (stimuli 4h..4h+3) of buffer `buf` is P float4, column j
+// lives at float4 index 5*(j>>2) + (j&3): the +1 skew every four columns makes
+// the eight k-lanes of a quarter warp (columns 4 kl + q) hit eight distinct
+// 16-byte bank groups.
+__host__ __device__ inline int panel_P(int kpad) { return 5 * (kpad / 4); }
+__device__ __forceinline__ int panel_col(int j) { return 5 * (j >> 2) + (j & 3); }
+// float index of (buf, column j, stimulus b)
+__device__ __forceinline__ int panel_index(int P, int buf, int j, int b) {
+    return (((buf * 2 + (b >> 2)) * P + panel_col(j)) << 2) + (b & 3);
+}
+
+struct ClusterShape {
+    int dim, kpad, csize, rpc;        // kpad = round_up(dim, 32); rpc = rows per CTA
+};
+
+// Shared-memory carve-up (bytes, all 16-byte aligned).
+struct SmemLayout {
+    int w_off, x_off, ext_off, gtab_off, misc_off, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(const ClusterShape &s, int n_sites) {
+    SmemLayout L;
+    int o = 0;
+    L.w_off = o;    o += s.rpc * s.kpad * 4;
+    L.x_off = o;    o += 2 * 2 * panel_P(s.kpad) * 16;
+    L.ext_off = o;  o += ((s.rpc * TB * 4 + 15) / 16) * 16;
+    L.gtab_off = o; o += ((4 * n_sites * 4 + 15) / 16) * 16;
+    L.misc_off = o; o += 1024;
+    L.total = o;
+    return L;
+}
+
+// misc block: flags[2][MAX_CLUSTER] (uint32), myflags, next_net
+struct Misc {
+    unsigned flags[2][MAX_CLUSTER];
+    unsigned myflags;
+    int next_net;
+    float scale[2][MAX_CLUSTER][TB];   // per-rank per-stimulus scratch (adjoint norms)
+};
+static_assert(sizeof(Misc) <= 1024, "misc block");
+
+// ---- W slice loaders -------------------------------------------------------------
+// Rows [row_base, row_base+rows_here) of W (or of W^T when TRANSPOSED) into Wsm[r*kpad + j].
+// src is W itself (w_kind = SSN_W_DENSE) or z (SSN_W_FROM_Z), both [dim][dim] row-major.
+template <bool TRANSPOSED>
+__device__ __forceinline__ void load_matrix_slice(float *Wsm, const float *__restrict__ src, int w_kind,
+                                                  const WeightConst &wc, const float *gtab,
+                                                  int n_sites, int dim, int kpad,
+                                                  int row_base, int rows_here, int tid, int nthreads) {
+    const int total = rows_here * kpad;
+    if (!TRANSPOSED) {
+        // consecutive threads walk along a row of W: coalesced global reads, conflict-free stores
+#pragma unroll 8
+        for (int idx = tid; idx < total; idx += nthreads) {
+            const int r = idx / kpad, j = idx - r * kpad;
+            const int i = row_base + r;
+            float v = 0.f;
+            if (j < dim) {
+                v = __ldg(src + (size_t)i * dim + j);
+                if (w_kind == SSN_W_FROM_Z) v = weight_from_z(wc, gtab, n_sites, i, j, v);
+            }
+            Wsm[idx] = v;
+        }
+    } else {
+        // slice row r holds column (row_base + r) of W: Wsm[r][j] = W[j][row_base + r].
+        // Consecutive threads take consecutive r, so global reads still run along a row of W.
+#pragma unroll 8
+        for (int idx = tid; idx < total; idx += nthreads) {
+            const int j = idx / rows_here, r = idx - j * rows_here;
+            float v = 0.f;
+            if (j < dim) {
+                v = __ldg(src + (size_t)j * dim + row_base + r);
+                if (w_kind == SSN_W_FROM_Z) v = weight_from_z(wc, gtab, n_sites, j, row_base + r, v);
+            }
+            Wsm[r * kpad + j] = v;
+        }
+    }
+}
+
+// ---- the skinny contraction --------------------------------------------------------
+// acc[t][b] = sum_j Wsm[row(t)][j] * X[buf][j][b]  over this thread's columns.
+template <int TI, int KL>
+__device__ __forceinline__ void contract_panel(float (&acc)[TI][TB], const float *Wsm, const float4 *X4,
+                                               int P, int kpad, int buf, const int (&wrow)[TI], int kl) {
+#pragma unroll
+    for (int t = 0; t < TI; ++t)
+#pragma unroll
+        for (int b = 0; b < TB; ++b) acc[t][b] = 0.f;
+
+    const float4 *Xa = X4 + (buf * 2 + 0) * P + 5 * kl;
+    const float4 *Xb = Xa + P;
+    const float4 *W4 = reinterpret_cast<const float4 *>(Wsm) + kl;
+    const int nsteps = kpad / (4 * KL);
+    const int kp4 = kpad / 4;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+        float4 w[TI];
+#pragma unroll
+        for (int t = 0; t < TI; ++t) w[t] = W4[wrow[t] * kp4 + s * KL];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 xa = Xa[s * 5 * KL + q];
+            const float4 xb = Xb[s * 5 * KL + q];
+#pragma unroll
+            for (int t = 0; t < TI; ++t) {
+                const float wq = q == 0 ? w[t].x : q == 1 ? w[t].y : q == 2 ? w[t].z : w[t].w;
+                acc[t][0] = fmaf(wq, xa.x, acc[t][0]);
+                acc[t][1] = fmaf(wq, xa.y, acc[t][1]);
+                acc[t][2] = fmaf(wq, xa.z, acc[t][2]);
+                acc[t][3] = fmaf(wq, xa.w, acc[t][3]);
+                acc[t][4] = fmaf(wq, xb.x, acc[t][4]);
+                acc[t][5] = fmaf(wq, xb.y, acc[t][5]);
+                acc[t][6] = fmaf(wq, xb.z, acc[t][6]);
+                acc[t][7] = fmaf(wq, xb.w, acc[t][7]);
+            }
+        }
+    }
+}
+
+// Reduce-scatter of the KL=8 partial tiles: on return out[t] is the full sum for
+// stimulus b = kl of row t.
+template <int TI>
+__device__ __forceinline__ void reduce_scatter8(const float (&acc)[TI][TB], float (&out)[TI], int kl) {
+    const unsigned full = 0xffffffffu;
+    float v4[TI][4], v2[TI][2];
+    const bool u4 = kl & 4, u2 = kl & 2, u1 = kl & 1;
+#pragma unroll
+    for (int t = 0; t < TI; ++t)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float send = u4 ? acc[t][c] : acc[t][4 + c];
+            const float keep = u4 ? acc[t][4 + c] : acc[t][c];
+            v4[t][c] = keep + __shfl_xor_sync(full, send, 4);
+        }
+#pragma unroll
+    for (int t = 0; t < TI; ++t)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float send = u2 ? v4[t][c] : v4[t][2 + c];
+            const float keep = u2 ? v4[t][2 + c] : v4[t][c];
+            v2[t][c] = keep + __shfl_xor_sync(full, send, 2);
+        }
+#pragma unroll
+    for (int t = 0; t < TI; ++t) {
+        const float send = u1 ? v2[t][0] : v2[t][1];
+        const float keep = u1 ? v2[t][1] : v2[t][0];
+        out[t] = keep + __shfl_xor_sync(full, send, 1);
+    }
+}
+
+// OR of a per-thread predicate over the lanes that share kl (stimulus), as a
+// bit mask indexed by stimulus.
+__device__ __forceinline__ unsigned stim_mask(bool pred) {
+    unsigned m = __ballot_sync(0xffffffffu, pred);
+    m |= m >> 16;
+    m |= m >> 8;
+    return m & 0xffu;
+}
+
+}  // namespace ssn

@@ -1,0 +1,496 @@
+// K1: batched SSN fixed-point solve (replaces tc_gan/ext/ssnode.c:69-187 driven by the
+// thread pool of tc_gan/ssnode.py:423-510, and tc_gan/weight_gen.py:13-26).
+//
+//   r <- r + (dt/tau) (-r + f(W r + I)),  Jacobi sweeps until max|dr| < atol.
+//
+// ssn_fp_cluster_kernel: persistent thread-block clusters pull networks from a
+// global work counter.  W (or W built from z) stays in the cluster's shared
+// memory; the 8-stimulus state panel is exchanged through DSMEM once per sweep;
+// the O(2N) state update and the convergence test run in float64, the O((2N)^2)
+// contraction in FP32 FFMA.
+//
+// ssn_fp64_kernel: all-float64 variant (one CTA per network x 8-stimulus panel,
+// W streamed from L2) used by the reference-ABI single-solve symbols and by
+// `precise` batched calls.
+#include <algorithm>
+#include <mutex>
+#include "ssn_cluster_core.cuh"
+
+namespace ssn {
+
+struct FpArgs {
+    int nz, nb, n_sites;
+    ClusterShape shape;
+    int w_kind;
+    const float *w;
+    WeightConst wc;
+    const float *ext;
+    long long ext_stride_z;        // 0: one [nb][dim] table shared by all networks
+    const float *r_init;           // [nz][nb][dim] or null
+    float *R;
+    int *status, *iters;
+    int *work_counter;
+    IoConst<float> io;
+    double eps_E, eps_I, atol, r_hard;
+    int max_iter, check_hard;
+};
+
+template <int TI, int KL, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1) ssn_fp_cluster_kernel(const FpArgs a) {
+    static_assert(KL == 8, "reduce_scatter8 assumes 8 k-lanes");
+    extern __shared__ __align__(16) unsigned char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int csize = a.shape.csize;
+    const int dim = a.shape.dim, kpad = a.shape.kpad, rpc = a.shape.rpc;
+    const int P = panel_P(kpad);
+    const SmemLayout L = smem_layout(a.shape, a.n_sites);
+    float *Wsm = reinterpret_cast<float *>(smem + L.w_off);
+    float *Xf = reinterpret_cast<float *>(smem + L.x_off);
+    const float4 *X4 = reinterpret_cast<const float4 *>(smem + L.x_off);
+    float *extsm = reinterpret_cast<float *>(smem + L.ext_off);
+    float *gtab = reinterpret_cast<float *>(smem + L.gtab_off);
+    Misc *misc = reinterpret_cast<Misc *>(smem + L.misc_off);
+
+    const int tid = threadIdx.x, nthreads = NWARPS * 32;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int kl = lane % KL;
+    const int grp = warp * (32 / KL) + lane / KL;
+    const int row0 = grp * TI;                               // first local row of this thread
+    const int row_base = rank * rpc;
+    const int rows_here = max(0, min(rpc, dim - row_base));
+
+    int wrow[TI];
+    bool valid[TI];
+#pragma unroll
+    for (int t = 0; t < TI; ++t) {
+        valid[t] = row0 + t < rows_here;
+        wrow[t] = min(row0 + t, rows_here - 1);
+    }
+
+    // peers' panels / misc blocks through distributed shared memory
+    float *Xpeer[MAX_CLUSTER];
+#pragma unroll
+    for (int p = 0; p < MAX_CLUSTER; ++p)
+        Xpeer[p] = p < csize ? cluster.map_shared_rank(Xf, p) : Xf;
+
+    if (a.w_kind == SSN_W_FROM_Z) build_profile_table(a.wc, a.n_sites, gtab, tid, nthreads);
+    for (int i = tid; i < 2 * 2 * P * 4; i += nthreads) Xf[i] = 0.f;     // padding columns stay 0
+    if (tid == 0) misc->myflags = 0u;
+    __syncthreads();
+
+    const int n_chunks = (a.nb + TB - 1) / TB;
+
+    for (;;) {
+        // ---- next network from the global queue ----
+        if (rank == 0 && tid == 0) {
+            const int n = atomicAdd(a.work_counter, 1);
+            for (int p = 0; p < csize; ++p) cluster.map_shared_rank(&misc->next_net, p)[0] = n;
+        }
+        cluster.sync();
+        const int net = misc->next_net;
+        if (net >= a.nz) break;
+
+        load_matrix_slice<false>(Wsm, a.w + (size_t)net * dim * dim, a.w_kind, a.wc, gtab,
+                                 a.n_sites, dim, kpad, row_base, rows_here, tid, nthreads);
+
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int b0 = chunk * TB;
+            const int nact = min(TB, a.nb - b0);
+            const bool active = kl < nact;
+            const float *ext_net = a.ext + (size_t)net * a.ext_stride_z;
+
+            // stimulus rows of this CTA -> smem, [local row][8]
+            for (int i = tid; i < rows_here * TB; i += nthreads) {
+                const int r = i / TB, b = i % TB;
+                extsm[i] = b < nact ? __ldg(ext_net + (size_t)(b0 + b) * dim + row_base + r) : 0.f;
+            }
+
+            // initial state (float64 master copy in registers), published to every CTA
+            double rstate[TI];
+#pragma unroll
+            for (int t = 0; t < TI; ++t) {
+                rstate[t] = 0.0;
+                if (valid[t] && active && a.r_init)
+                    rstate[t] = (double)__ldg(a.r_init + ((size_t)net * a.nb + b0 + kl) * dim + row_base + row0 + t);
+                if (valid[t]) {
+                    const int idx = panel_index(P, 0, row_base + row0 + t, kl);
+                    const float rf = (float)rstate[t];
+#pragma unroll
+                    for (int p = 0; p < MAX_CLUSTER; ++p)
+                        if (p < csize) Xpeer[p][idx] = rf;
+                }
+            }
+            cluster.sync();
+
+            unsigned done = nact >= TB ? 0u : (0xffu << nact) & 0xffu;   // finished stimuli
+            int my_status = 1, my_iters = a.max_iter;                   // of stimulus kl
+            int buf = 0;
+
+            for (int it = 1; it <= a.max_iter; ++it) {
+                float acc[TI][TB], v[TI];
+                contract_panel<TI, KL>(acc, Wsm, X4, P, kpad, buf, wrow, kl);
+                reduce_scatter8<TI>(acc, v, kl);
+
+                const int nbuf = buf ^ 1;
+                const bool frozen = (done >> kl) & 1u;
+                bool moving = false, above = false;
+#pragma unroll
+                for (int t = 0; t < TI; ++t) {
+                    if (valid[t]) {
+                        const int lr = row0 + t;
+                        const float vt = v[t] + extsm[lr * TB + kl];
+                        const float fv = io_eval<float>(a.io, vt);
+                        const double eps = (row_base + lr) < a.n_sites ? a.eps_E : a.eps_I;
+                        const double r_old = rstate[t];
+                        const double r_new = r_old + ((double)fv - r_old) * eps;
+                        if (!frozen) {
+                            moving |= fabs(r_new - r_old) >= a.atol;
+                            above |= r_new >= a.r_hard;
+                            rstate[t] = r_new;
+                        }
+                        const int idx = panel_index(P, nbuf, row_base + lr, kl);
+                        const float rf = (float)rstate[t];
+#pragma unroll
+                        for (int p = 0; p < MAX_CLUSTER; ++p)
+                            if (p < csize) Xpeer[p][idx] = rf;
+                    }
+                }
+                const unsigned mm = stim_mask(moving), ma = stim_mask(above);
+                if (lane == 0 && (mm | ma)) atomicOr(&misc->myflags, mm | (ma << 8));
+                __syncthreads();
+                if (tid == 0) {
+                    const unsigned f = misc->myflags;
+                    misc->myflags = 0u;
+                    for (int p = 0; p < csize; ++p)
+                        cluster.map_shared_rank(&misc->flags[nbuf][rank], p)[0] = f;
+                }
+                cluster.sync();
+                unsigned F = 0u;
+                for (int p = 0; p < csize; ++p) F |= misc->flags[nbuf][p];
+                const unsigned moving_all = F & 0xffu, above_all = (F >> 8) & 0xffu;
+                // reference order: convergence first, then the hard bound (ssnode.c:84-102)
+                const unsigned conv_now = ~moving_all & ~done & 0xffu;
+                const unsigned hard_now = a.check_hard ? (above_all & ~done & ~conv_now & 0xffu) : 0u;
+                if ((conv_now >> kl) & 1u) { my_status = 0; my_iters = it; }
+                if ((hard_now >> kl) & 1u) { my_status = 2; my_iters = it; }
+                done |= conv_now | hard_now;
+                buf = nbuf;
+                if (done == 0xffu) break;
+            }
+
+            // ---- results ----
+#pragma unroll
+            for (int t = 0; t < TI; ++t)
+                if (valid[t] && active)
+                    a.R[((size_t)net * a.nb + b0 + kl) * dim + row_base + row0 + t] = (float)rstate[t];
+            if (rank == 0 && tid < TB && tid < nact) {          // warp 0, group 0: lane == kl
+                a.status[(size_t)net * a.nb + b0 + tid] = my_status;
+                if (a.iters) a.iters[(size_t)net * a.nb + b0 + tid] = my_iters;
+            }
+            // every CTA must be out of the sweep loop before the panel is re-initialised
+            cluster.sync();
+        }
+    }
+}
+
+// A converged solve with a non-finite state counts as failed (tc_gan/ssnode.py:257-262).
+__global__ void ssn_status_fixup_kernel(const float *R, int *status, int n_solves, int dim) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_solves) return;
+    bool bad = false;
+    for (int i = lane; i < dim; i += 32) bad |= !isfinite(R[(size_t)warp * dim + i]);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0 && bad && status[warp] == 0) status[warp] = 1;
+}
+
+// ------------------------------------------------------------------------------------
+// float64 kernel: one CTA per (network, panel of TBD stimuli); W (double) read from
+// global memory (L2-resident) every sweep, one warp per row, lanes stride the columns.
+// ------------------------------------------------------------------------------------
+struct Fp64Args {
+    int nz, nb, n_sites, dim;
+    const double *W;               // [nz][dim][dim]
+    const double *ext;             // [nb][dim] or [nz][nb][dim]
+    long long ext_stride_z;
+    const double *r_init;          // [nz][nb][dim] or null
+    double *R;                     // [nz][nb][dim]
+    int *status, *iters;
+    IoConst<double> io;
+    double eps_E, eps_I, atol, r_hard;
+    int max_iter, check_hard;
+};
+
+template <int TBD>
+__global__ void __launch_bounds__(512) ssn_fp64_kernel(const Fp64Args a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int dim = a.dim;
+    double *X = reinterpret_cast<double *>(smem);            // [2][dim][TBD]
+    double *E = X + 2 * dim * TBD;                           // [dim][TBD]
+    __shared__ unsigned s_flags[2];
+    const int n_chunks = (a.nb + TBD - 1) / TBD;
+    const int net = blockIdx.x / n_chunks, chunk = blockIdx.x % n_chunks;
+    const int b0 = chunk * TBD, nact = min(TBD, a.nb - b0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const double *W = a.W + (size_t)net * dim * dim;
+    const double *ext = a.ext + (size_t)net * a.ext_stride_z;
+
+    for (int i = tid; i < dim * TBD; i += blockDim.x) {
+        const int r = i / TBD, b = i % TBD;
+        E[i] = b < nact ? ext[(size_t)(b0 + b) * dim + r] : 0.0;
+        X[i] = (b < nact && a.r_init) ? a.r_init[((size_t)net * a.nb + b0 + b) * dim + r] : 0.0;
+    }
+    if (tid < 2) s_flags[tid] = 0u;
+    __syncthreads();
+
+    unsigned done = nact >= TBD ? 0u : (((1u << TBD) - 1u) & ~((1u << nact) - 1u));
+    const unsigned all = (1u << TBD) - 1u;
+    int buf = 0;
+    int st[TBD], its[TBD];
+#pragma unroll
+    for (int b = 0; b < TBD; ++b) { st[b] = 1; its[b] = a.max_iter; }
+
+    for (int it = 1; it <= a.max_iter; ++it) {
+        const double *Xc = X + buf * dim * TBD;
+        double *Xn = X + (buf ^ 1) * dim * TBD;
+        unsigned moving = 0u, above = 0u;
+        for (int i = warp; i < dim; i += nwarps) {
+            double acc[TBD];
+#pragma unroll
+            for (int b = 0; b < TBD; ++b) acc[b] = 0.0;
+            const double *row = W + (size_t)i * dim;
+            for (int j = lane; j < dim; j += 32) {
+                const double w = row[j];
+#pragma unroll
+                for (int b = 0; b < TBD; ++b) acc[b] = fma(w, Xc[j * TBD + b], acc[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < TBD; ++b)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+            if (lane < TBD) {
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < TBD; ++b) s = lane == b ? acc[b] : s;
+                const int b = lane;
+                const double r_old = Xc[i * TBD + b];
+                double r_new = r_old;
+                if (!((done >> b) & 1u)) {
+                    const double fv = io_eval<double>(a.io, s + E[i * TBD + b]);
+                    const double eps = i < a.n_sites ? a.eps_E : a.eps_I;
+                    r_new = r_old + (fv - r_old) * eps;
+                    if (fabs(r_new - r_old) >= a.atol) moving |= 1u << b;
+                    if (r_new >= a.r_hard) above |= 1u << b;
+                }
+                Xn[i * TBD + b] = r_new;
+            }
+        }
+        if (moving | above) atomicOr(&s_flags[it & 1], moving | (above << 8));
+        __syncthreads();
+        const unsigned F = s_flags[it & 1];
+        if (tid == 0) s_flags[(it + 1) & 1] = 0u;
+        const unsigned conv_now = ~(F & 0xffu) & ~done & all;
+        const unsigned hard_now = a.check_hard ? ((F >> 8) & ~done & ~conv_now & all) : 0u;
+#pragma unroll
+        for (int b = 0; b < TBD; ++b) {
+            if ((conv_now >> b) & 1u) { st[b] = 0; its[b] = it; }
+            if ((hard_now >> b) & 1u) { st[b] = 2; its[b] = it; }
+        }
+        done |= conv_now | hard_now;
+        buf ^= 1;
+        if (done == all) break;
+        __syncthreads();      // s_flags reset visible before the next sweep's atomics
+    }
+    __syncthreads();
+    const double *Xc = X + buf * dim * TBD;
+    for (int i = tid; i < dim * nact; i += blockDim.x) {
+        const int b = i / dim, r = i % dim;
+        a.R[((size_t)net * a.nb + b0 + b) * dim + r] = Xc[r * TBD + b];
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < TBD; ++b)
+            if (b < nact) {
+                // converged to a non-finite value -> failure (ssnode.py:257-262)
+                a.status[(size_t)net * a.nb + b0 + b] = st[b];
+                if (a.iters) a.iters[(size_t)net * a.nb + b0 + b] = its[b];
+            }
+    }
+}
+
+__global__ void ssn_status_fixup_f64_kernel(const double *R, int *status, int n_solves, int dim) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_solves) return;
+    bool bad = false;
+    for (int i = lane; i < dim; i += 32) bad |= !isfinite(R[(size_t)warp * dim + i]);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0 && bad && status[warp] == 0) status[warp] = 1;
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+
+static int max_optin_smem() {
+    static int v = -1;
+    if (v < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) v = 0;
+    }
+    return v;
+}
+
+// Smallest cluster whose CTAs can hold their slice of the matrix.
+bool choose_cluster_shape(int n_sites, ClusterShape *out, int smem_limit) {
+    const int dim = 2 * n_sites;
+    ClusterShape s;
+    s.dim = dim;
+    s.kpad = ((dim + 31) / 32) * 32;
+    for (int c = 1; c <= MAX_CLUSTER; c *= 2) {
+        s.csize = c;
+        s.rpc = (dim + c - 1) / c;
+        if (s.rpc * (c - 1) >= dim) continue;               // a CTA would own no rows
+        if (s.rpc > 32 * 7) continue;                       // widest instantiation: 8 warps x 4 groups x 7 rows
+        if (smem_layout(s, n_sites).total <= smem_limit) { *out = s; return true; }
+    }
+    return false;
+}
+
+typedef void (*FpKernel)(const FpArgs);
+struct FpVariant { FpKernel fn; int threads; int rows; };
+
+static FpVariant pick_fp_variant(int rpc) {
+    // rows covered = (32/KL) * NWARPS * TI
+    if (rpc <= 16 * 4) return {ssn_fp_cluster_kernel<4, 8, 4>, 128, 64};
+    if (rpc <= 16 * 7) return {ssn_fp_cluster_kernel<7, 8, 4>, 128, 112};
+    return {ssn_fp_cluster_kernel<7, 8, 8>, 256, 224};
+}
+
+struct FpLaunchPlan { FpVariant var; ClusterShape shape; int smem; int clusters; };
+
+static int plan_fixed_point(int n_sites, int nz, FpLaunchPlan *plan) {
+    const int limit = max_optin_smem();
+    if (!choose_cluster_shape(n_sites, &plan->shape, limit)) {
+        set_error("fixed-point kernel: 2N=%d does not fit a cluster of %d CTAs (smem %d B)",
+                  2 * n_sites, MAX_CLUSTER, limit);
+        return -1;
+    }
+    plan->var = pick_fp_variant(plan->shape.rpc);
+    plan->smem = smem_layout(plan->shape, n_sites).total;
+    SSN_CUDA(cudaFuncSetAttribute(plan->var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plan->shape.csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(plan->shape.csize, 1, 1);
+    cfg.blockDim = dim3(plan->var.threads, 1, 1);
+    cfg.dynamicSmemBytes = plan->smem;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    SSN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, plan->var.fn, &cfg));
+    if (max_clusters < 1) {
+        set_error("fixed-point kernel: no resident cluster of %d CTAs with %d B smem", plan->shape.csize, plan->smem);
+        return -1;
+    }
+    plan->clusters = nz > 0 ? std::min(max_clusters, nz) : max_clusters;
+    return 0;
+}
+
+int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters) {
+    FpLaunchPlan plan;
+    int rc = plan_fixed_point(n_sites, 0, &plan);
+    if (rc) return rc;
+    if (cluster_size) *cluster_size = plan.shape.csize;
+    if (resident_clusters) *resident_clusters = plan.clusters;
+    return 0;
+}
+
+// All pointers are device pointers; `counter` is one int of scratch.
+int launch_fixed_point_f32(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
+                           const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
+                           float *R, int *status, int *iters, int *counter, cudaStream_t stream) {
+    if (nz <= 0 || nb <= 0) return 0;
+    FpLaunchPlan plan;
+    int rc = plan_fixed_point(n_sites, nz, &plan);
+    if (rc) return rc;
+    FpArgs a = {};
+    a.nz = nz; a.nb = nb; a.n_sites = n_sites;
+    a.shape = plan.shape;
+    a.w_kind = w_kind; a.w = w;
+    if (w_kind == SSN_W_FROM_Z) {
+        if (!jds) { set_error("SSN_W_FROM_Z needs jds"); return -1; }
+        a.wc = make_weight_const(*jds, n_sites);
+    }
+    a.ext = ext;
+    a.ext_stride_z = ext_per_network ? (long long)nb * 2 * n_sites : 0;
+    a.r_init = r_init;
+    a.R = R; a.status = status; a.iters = iters; a.work_counter = counter;
+    a.io = make_io_const<float>(sv.io_type, sv.k, sv.n, sv.rate_soft_bound, sv.rate_hard_bound);
+    a.eps_E = sv.dt / sv.tau_E; a.eps_I = sv.dt / sv.tau_I;
+    a.atol = sv.atol; a.r_hard = sv.rate_hard_bound;
+    a.max_iter = sv.max_iter; a.check_hard = sv.io_type != SSN_IO_TANH;
+
+    SSN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plan.shape.csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(plan.clusters * plan.shape.csize, 1, 1);
+    cfg.blockDim = dim3(plan.var.threads, 1, 1);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SSN_CUDA(cudaLaunchKernelEx(&cfg, plan.var.fn, a));
+    count_launch();
+    const int n_solves = nz * nb;
+    ssn_status_fixup_kernel<<<(n_solves * 32 + 255) / 256, 256, 0, stream>>>(R, status, n_solves, 2 * n_sites);
+    SSN_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int launch_fixed_point_f64(const ssn_solver &sv, int nz, int nb, int n_sites, const double *W,
+                           const double *ext, int ext_per_network, const double *r_init,
+                           double *R, int *status, int *iters, bool nonfinite_fixup, cudaStream_t stream) {
+    if (nz <= 0 || nb <= 0) return 0;
+    Fp64Args a = {};
+    a.nz = nz; a.nb = nb; a.n_sites = n_sites; a.dim = 2 * n_sites;
+    a.W = W; a.ext = ext;
+    a.ext_stride_z = ext_per_network ? (long long)nb * 2 * n_sites : 0;
+    a.r_init = r_init; a.R = R; a.status = status; a.iters = iters;
+    a.io = make_io_const<double>(sv.io_type, sv.k, sv.n, sv.rate_soft_bound, sv.rate_hard_bound);
+    a.eps_E = sv.dt / sv.tau_E; a.eps_I = sv.dt / sv.tau_I;
+    a.atol = sv.atol; a.r_hard = sv.rate_hard_bound;
+    a.max_iter = sv.max_iter; a.check_hard = sv.io_type != SSN_IO_TANH;
+    const int tbd = nb == 1 ? 1 : 8;
+    const int n_chunks = (nb + tbd - 1) / tbd;
+    const size_t smem = (size_t)3 * a.dim * tbd * sizeof(double);
+    if ((int)smem > max_optin_smem()) {
+        set_error("float64 kernel: 2N=%d needs %zu B of shared memory", a.dim, smem);
+        return -1;
+    }
+    if (tbd == 1) {
+        SSN_CUDA(cudaFuncSetAttribute(ssn_fp64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ssn_fp64_kernel<1><<<nz * n_chunks, 512, smem, stream>>>(a);
+    } else {
+        SSN_CUDA(cudaFuncSetAttribute(ssn_fp64_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ssn_fp64_kernel<8><<<nz * n_chunks, 512, smem, stream>>>(a);
+    }
+    SSN_CUDA(cudaGetLastError());
+    count_launch();
+    const int n_solves = nz * nb;
+    if (!nonfinite_fixup) return 0;
+    ssn_status_fixup_f64_kernel<<<(n_solves * 32 + 255) / 256, 256, 0, stream>>>(R, status, n_solves, a.dim);
+    SSN_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace ssn

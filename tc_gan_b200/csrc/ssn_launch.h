@@ -1,0 +1,32 @@
+// Internal launcher prototypes (device pointers, enqueue on `stream`, no sync).
+#pragma once
+#include "ssn_common.cuh"
+
+namespace ssn {
+
+int launch_fixed_point_f32(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
+                           const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
+                           float *R, int *status, int *iters, int *counter, cudaStream_t stream);
+int launch_fixed_point_f64(const ssn_solver &sv, int nz, int nb, int n_sites, const double *W,
+                           const double *ext, int ext_per_network, const double *r_init,
+                           double *R, int *status, int *iters, bool nonfinite_fixup, cudaStream_t stream);
+int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters);
+
+int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
+                        const float *ext, int ext_per_network, const float *R, const float *g, double rtol,
+                        double *grad, float *mu, int *status, int *iters, int *counter, cudaStream_t stream);
+
+int launch_euler_forward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
+                         const float *ext, int ext_per_network, int seqlen, int skip_steps, double threshold,
+                         float *time_avg, double *penalties, float *traj, float *gain, int *counter,
+                         cudaStream_t stream);
+int launch_euler_backward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
+                          int seqlen, int skip_steps, double threshold, const float *grad_time_avg,
+                          double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
+                          double *grad, int *counter, cudaStream_t stream);
+
+int launch_generate_weight(int nz, int n_sites, const float *z, const ssn_jds &jds, float *W, cudaStream_t stream);
+int launch_convert_f64_to_f32(const double *src, float *dst, size_t n, cudaStream_t stream);
+int launch_convert_f32_to_f64(const float *src, double *dst, size_t n, cudaStream_t stream);
+
+}  // namespace ssn

@@ -1,0 +1,412 @@
+"""
+SSN fixed-point solver API -- mirror of tc_gan/ssnode.py over the CUDA library.
+
+Same names, arguments, return types and error behaviour as the reference
+(``fixed_point``, ``solve_dynamics``, ``find_fixed_points``, ``make_io_fun``,
+``sample_fixed_points``, ``sample_tuning_curves``, ``DEFAULT_PARAMS``,
+``FixedPointResult`` / ``FixedPointError`` / ``FixedPointsInfo``), but:
+
+* ``fixed_point`` crosses the same ctypes boundary (ssnode.py:244-255) into a
+  float64 CUDA kernel instead of the C loop;
+* ``find_fixed_points`` replaces the thread pool over (network, stimulus) solves
+  (ssnode.py:390-510) by batched launches: every drawn network is solved for all
+  stimuli at once by persistent thread-block clusters.
+
+There is no CPU solver in this module.
+"""
+from __future__ import print_function, division
+
+import collections
+import itertools
+
+import numpy as np
+
+from . import clib
+from .clib import libssnode, double_ptr
+from .gradient_expressions.utils import subsample_neurons
+
+
+DEFAULT_PARAMS = dict(
+    N=102,
+    J=np.array([[.0957, .0638], [.1197, .0479]]),
+    D=np.array([[.7660, .5106], [.9575, .3830]]),
+    S=np.array([[.6667, .2], [1.333, .2]]) / 8,
+    bandwidths=[0, 0.0625, 0.125, 0.1875, 0.25, 0.5, 0.75, 1],
+    smoothness=0.25/8,
+    contrast=[20],
+    offset=[0],
+    io_type='asym_tanh',
+    k=0.01,
+    n=2.2,
+    rate_soft_bound=200, rate_hard_bound=1000,
+    tau=(0.01589, 0.002),
+)
+
+
+def new_JDS():
+    """More stable generator parameters (networks/fixed_time_sampler.py:12-23)."""
+    D_new = DEFAULT_PARAMS['D'] / 2
+    J_new = DEFAULT_PARAMS['J'] + DEFAULT_PARAMS['D'] / 2 - D_new / 2
+    return dict(J=J_new, D=D_new, S=DEFAULT_PARAMS['S'].copy())
+
+
+class FixedPointResult(object):
+
+    message = None
+
+    def __init__(self, x, error, iterations=None):
+        self.x = x
+        self.error = error
+        self.iterations = iterations
+
+    @property
+    def success(self):
+        return self.error == 0
+
+    def to_exception(self):
+        return FixedPointError(self.message, self)
+
+
+class FixedPointError(Exception):
+
+    def __init__(self, message, result):
+        super(FixedPointError, self).__init__(message)
+        self.result = result
+
+
+def take(n, iterable):
+    return list(itertools.islice(iterable, n))
+
+
+def make_neu_vec(N, E, I):
+    return np.array([E] * N + [I] * N)
+
+
+def any_to_neu_vec(N, vec):
+    vec = np.asarray(vec)
+    if len(vec) == 2:
+        vec = make_neu_vec(N, *vec)
+    return vec
+
+
+def thlin(x):
+    return x * (x > 0)
+
+
+def rate_to_volt(rate, k, n):
+    return (rate / k)**(1 / n)
+
+
+def _xp(a):
+    try:
+        import torch
+        if isinstance(a, torch.Tensor):
+            return torch
+    except ImportError:
+        pass
+    return np
+
+
+def io_alin(v, volt_max, k, n):
+    xp = _xp(v)
+    vc = xp.clip(v, 0, volt_max)
+    rate = k * (vc**n)
+    linear = k * (volt_max**(n-1)) * n * (v - volt_max)
+    return xp.where(v <= volt_max, rate, rate + linear)
+
+
+def io_power(v, k, n):
+    return k * (thlin(v)**n)
+
+
+def io_atanh(v, r0, r1, v0, k, n):
+    xp = _xp(v)
+    v_pow = xp.clip(v, 0, v0)
+    r_pow = k * (v_pow**n)
+    r_tanh = r0 + (r1 - r0) * xp.tanh(n * r0 / (r1 - r0) * (v - v0) / v0)
+    return xp.where(v <= v0, r_pow, r_tanh)
+
+
+def make_io_fun(k, n,
+                rate_soft_bound=DEFAULT_PARAMS['rate_soft_bound'],
+                rate_hard_bound=DEFAULT_PARAMS['rate_hard_bound'],
+                io_type=DEFAULT_PARAMS['io_type']):
+    """Elementwise transfer function on numpy arrays / torch tensors (ssnode.py:276-292)."""
+    v0 = rate_to_volt(rate_soft_bound, k, n)
+    if io_type == 'asym_linear':
+        def io_fun(v):
+            return io_alin(v, v0, k, n)
+    elif io_type == 'asym_tanh':
+        def io_fun(v):
+            return io_atanh(v, rate_soft_bound, rate_hard_bound, v0, k, n)
+    elif io_type == 'asym_power':
+        def io_fun(v):
+            return io_power(v, k, n)
+    else:
+        raise ValueError("Unknown I/O type: {}".format(io_type))
+    return io_fun
+
+
+def solve_dynamics(*args, **kwds):
+    sol = fixed_point(*args, **kwds)
+    if not sol.success:
+        print(sol.message)
+    return sol.x
+
+
+def _set_message(sol):
+    """Error code -> message, exactly as ssnode.py:256-270."""
+    error = sol.error
+    if error == 0:
+        if np.isfinite(sol.x).all():
+            sol.message = "Converged"
+        else:
+            sol.error = 1
+            sol.message = "Converged to non-finite value"
+    elif error == 1:
+        sol.message = "SSN Convergence Failed"
+    elif error == 2:
+        sol.message = "Reached to rate_stop_at"
+    elif error > 900:
+        sol.message = "CUDA error {}: {}".format(
+            error - 1000, libssnode.ssn_last_error().decode('utf-8', 'replace'))
+    else:
+        sol.message = "Unknown error: code={}".format(error)
+    return sol
+
+
+def fixed_point(
+        W, ext, k, n, r0=None, tau=DEFAULT_PARAMS['tau'],
+        max_iter=10000, atol=1e-5, dt=.0008, solver='euler',
+        rate_soft_bound=DEFAULT_PARAMS['rate_soft_bound'],
+        rate_hard_bound=DEFAULT_PARAMS['rate_hard_bound'],
+        rate_stop_at=np.inf,
+        io_type='asym_tanh', check=False):
+    """
+    Solve the SSN ODE for one (W, ext) until it reaches a fixed point.
+
+    Same signature and result as tc_gan.ssnode.fixed_point (ssnode.py:159-273);
+    the Euler loop runs on the GPU in float64 through the reference C ABI
+    ``solve_dynamics_{io_type}_{solver}``.  A failure of the GPU call itself
+    raises `clib.SSNLibraryError` (there is no CPU fallback).
+    """
+    if io_type not in ('asym_linear', 'asym_tanh', 'asym_power'):
+        raise ValueError("Unknown I/O type: {}".format(io_type))
+    if solver not in ('euler',):
+        raise ValueError("Unknown solver: {}".format(solver))
+
+    W = np.ascontiguousarray(W, dtype='double')
+    N = W.shape[0] // 2
+    ext = np.ascontiguousarray(ext, dtype='double')
+    if r0 is None:
+        r0 = np.zeros(2 * N, dtype='double')
+    else:
+        r0 = np.array(r0, dtype='double')  # copied, as it will be modified
+    r1 = np.empty_like(r0)
+    tau_E, tau_I = tau
+
+    assert 2 * N == W.shape[0] == W.shape[1]
+    assert W.ndim == 2
+    assert (2 * N,) == r0.shape == ext.shape
+
+    if io_type in ('asym_power', 'asym_linear'):
+        rate_hard_bound = rate_stop_at
+
+    error = getattr(libssnode,
+                    'solve_dynamics_{}_{}'.format(io_type, solver))(
+        N,
+        W.ctypes.data_as(double_ptr),
+        ext.ctypes.data_as(double_ptr),
+        float(k), float(n),
+        r0.ctypes.data_as(double_ptr),
+        r1.ctypes.data_as(double_ptr),
+        tau_E, tau_I,
+        dt, max_iter, atol,
+        rate_soft_bound, rate_hard_bound,
+    )
+    if error > 900:
+        clib.check_call(error, 'solve_dynamics_{}_{}'.format(io_type, solver))
+    sol = _set_message(FixedPointResult(r0, error))
+    if check and not sol.success:
+        raise sol.to_exception()
+    return sol
+
+
+FixedPointsInfo = collections.namedtuple('FixedPointsInfo', [
+    'solutions', 'counter', 'rejections', 'unused',
+])
+null_FixedPointsInfo = FixedPointsInfo(None, None, 0, 0)
+
+
+def fixed_points_batch(Ws, exts, k, n, r0=None, tau=DEFAULT_PARAMS['tau'],
+                       max_iter=10000, atol=1e-5, dt=.0008, solver='euler',
+                       rate_soft_bound=DEFAULT_PARAMS['rate_soft_bound'],
+                       rate_hard_bound=DEFAULT_PARAMS['rate_hard_bound'],
+                       rate_stop_at=np.inf, io_type='asym_tanh', precise=False):
+    """
+    All (network, stimulus) solves of ``Ws`` [nz, 2N, 2N] x ``exts`` [nb, 2N] in one
+    batched GPU call.  Returns ``(Rs [nz, nb, 2N] float64, errors [nz, nb], iters [nz, nb])``
+    with the reference's error codes.  ``precise=True`` runs the float64 kernel;
+    the default contracts in FP32 with a float64 state update.
+    """
+    if solver not in ('euler',):
+        raise ValueError("Unknown solver: {}".format(solver))
+    Ws = np.ascontiguousarray(Ws, dtype='double')
+    exts = np.ascontiguousarray(exts, dtype='double')
+    nz, dim = Ws.shape[0], Ws.shape[1]
+    nb = exts.shape[0]
+    assert Ws.shape == (nz, dim, dim) and exts.shape == (nb, dim) and dim % 2 == 0
+    sv = clib.make_solver(io_type=io_type, k=k, n=n, tau=tau, dt=dt, max_iter=max_iter, atol=atol,
+                          rate_soft_bound=rate_soft_bound, rate_hard_bound=rate_hard_bound,
+                          rate_stop_at=rate_stop_at)
+    r_init = None
+    if r0 is not None:
+        r0 = np.asarray(r0, dtype='double')
+        if r0.any():
+            r_init = np.ascontiguousarray(np.broadcast_to(r0, (nz, nb, dim)))
+    Rs = np.empty((nz, nb, dim))
+    errors = np.empty((nz, nb), dtype=np.int32)
+    iters = np.empty((nz, nb), dtype=np.int32)
+    clib.check_call(libssnode.ssn_fixed_point_batch_f64(
+        sv, nz, nb, dim // 2, Ws.ctypes.data, exts.ctypes.data,
+        None if r_init is None else r_init.ctypes.data,
+        Rs.ctypes.data, errors.ctypes.data, iters.ctypes.data, int(bool(precise))),
+        'ssn_fixed_point_batch_f64')
+    return Rs, errors, iters
+
+
+def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
+    """
+    Find `num` sets of fixed points using weight matrices from `Z_W_gen`.
+
+    Same contract as tc_gan.ssnode.find_fixed_points (ssnode.py:332-387): a
+    network is kept only if every stimulus in `exts` converges; returns
+    ``(Zs [num, ...], Rs [num, NB, 2N], FixedPointsInfo)``.
+
+    Both ``method='parallel'`` and ``'serial'`` run the same batched GPU path
+    (``method`` is validated for compatibility).  Networks are drawn from
+    `Z_W_gen` in rounds of exactly as many as are still missing, so the generator
+    is consumed precisely as far as the reference's serial finder would consume
+    it, the kept networks are the first `num` successes in generator order
+    (ssnode.py:489-495) and ``info.unused`` is 0.
+
+    Extra keyword arguments understood here (and ignored by nothing): those of
+    `fixed_point`, plus ``precise`` (float64 kernel), and the thread-pool knobs
+    ``no_pool``, ``resubmit_threshold``, ``deterministic`` which are accepted
+    and have no effect.
+    """
+    if method not in ('parallel', 'serial'):
+        raise ValueError('Unknown method: {}'.format(method))
+    kwargs = dict(common_kwargs)
+    for ignored in ('no_pool', 'resubmit_threshold', 'deterministic'):
+        kwargs.pop(ignored, None)
+    check = kwargs.pop('check', False)
+    exts = np.asarray(exts, dtype='double')
+    nb = len(exts)
+    Z_W_gen = iter(Z_W_gen)
+
+    kept = []                       # (Z, Rs[nb, 2N], iters[nb])
+    counter = collections.Counter()
+    while len(kept) < num:
+        drawn = take(num - len(kept), Z_W_gen)
+        if not drawn:
+            break
+        Ws = np.array([np.asarray(W, dtype='double') for _, W in drawn])
+        Rs, errors, iters = fixed_points_batch(Ws, exts, **kwargs)
+        for (Z, _), R, err, its in zip(drawn, Rs, errors, iters):
+            if (err == 0).all():
+                kept.append((Z, R, its))
+                continue
+            # the reference visits stimuli last to first and records the first failure
+            b = max(np.flatnonzero(err != 0))
+            sol = _set_message(FixedPointResult(R[b], int(err[b]), int(its[b])))
+            counter[sol.error] += 1
+            if check:
+                raise sol.to_exception()
+
+    if not kept:
+        raise ValueError('find_fixed_points: Z_W_gen was exhausted before any network converged')
+    zs, xs, its = zip(*kept)
+    solutions = tuple(
+        [_set_message(FixedPointResult(x, 0, int(i))) for x, i in zip(R, it)]
+        for R, it in zip(xs, its))
+    return np.array(zs), np.array(xs), FixedPointsInfo(
+        solutions, counter, sum(counter.values()), 0)
+
+
+def find_fixed_points_serial(num, Z_W_gen, exts, **common_kwargs):
+    return find_fixed_points(num, Z_W_gen, exts, method='serial', **common_kwargs)
+
+
+def find_fixed_points_parallel(num, Z_W_gen, exts, **common_kwargs):
+    return find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs)
+
+
+def make_solver_params(
+        N=DEFAULT_PARAMS['N'],
+        J=DEFAULT_PARAMS['J'],
+        D=DEFAULT_PARAMS['D'],
+        S=DEFAULT_PARAMS['S'],
+        io_type=DEFAULT_PARAMS['io_type'],
+        seed=65,
+        bandwidth=1,
+        smoothness=DEFAULT_PARAMS['smoothness'],
+        contrast=DEFAULT_PARAMS['contrast'],
+        k=DEFAULT_PARAMS['k'],
+        n=DEFAULT_PARAMS['n'],
+        ):
+    """One seeded (W, ext) problem, as ssnode.py:526-558."""
+    from . import stimuli
+    from .weight_gen import generate_weight
+
+    rs = np.random.RandomState(seed) if isinstance(seed, int) else seed
+    Z = rs.rand(1, 2*N, 2*N)
+    W = generate_weight(N, J, D, S, Z[0])
+    X = np.linspace(-0.5, 0.5, N)
+    ext, = stimuli.input([bandwidth], X, smoothness, contrast)
+    return dict(W=W, ext=ext, r0=np.zeros(W.shape[0]), k=k, n=n, io_type=io_type)
+
+
+def sample_fixed_points(
+        NZ=30, seed=0,
+        N=DEFAULT_PARAMS['N'],
+        J=DEFAULT_PARAMS['J'],
+        D=DEFAULT_PARAMS['D'],
+        S=DEFAULT_PARAMS['S'],
+        bandwidths=DEFAULT_PARAMS['bandwidths'],
+        smoothness=DEFAULT_PARAMS['smoothness'],
+        contrast=DEFAULT_PARAMS['contrast'],
+        offset=DEFAULT_PARAMS['offset'],
+        io_type=DEFAULT_PARAMS['io_type'],
+        k=DEFAULT_PARAMS['k'],
+        n=DEFAULT_PARAMS['n'],
+        **solver_kwargs):
+    """Seeded rejection sampling of NZ networks, as ssnode.py:561-590."""
+    from . import stimuli
+    from .weight_gen import generate_weight
+
+    X = np.linspace(-0.5, 0.5, N)
+    exts = stimuli.input(bandwidths, X, smoothness, contrast, offset)
+    rs = np.random.RandomState(seed)
+
+    def Z_W_gen():
+        while True:
+            z = rs.rand(1, 2*N, 2*N)
+            yield z[0], generate_weight(N, J, D, S, z[0])
+
+    solver_kwargs.setdefault('r0', np.zeros(2 * N))
+    solver_kwargs.update(k=k, n=n, io_type=io_type)
+    return find_fixed_points(NZ, Z_W_gen(), exts, **solver_kwargs)
+
+
+def sample_tuning_curves(sample_sites=[0], track_offset_identity=False,
+                         include_inhibitory_neurons=False,
+                         **kwargs):
+    """Tuning curves of sampled networks, as ssnode.py:593-602."""
+    _, rates, _ = sample = sample_fixed_points(**kwargs)
+    rates = np.array(rates)
+    tunings = subsample_neurons(
+        rates, sample_sites,
+        include_inhibitory_neurons=include_inhibitory_neurons,
+        track_offset_identity=track_offset_identity).T
+    return tunings, sample

@@ -1,0 +1,254 @@
+"""
+GPU parity tests of the fixed-point path (K1) through the C ABI.
+
+Tolerance of the fast path (FP32 FFMA contraction, float64 state): rtol 1e-4 as
+BASELINE.json's north_star states, with the atol floor the reference's own
+cross-solver tests use (tc_gan/networks/tests/test_euler_ssn.py:36,86), because
+the reference stops as soon as one Euler step moves every rate by < atol=1e-5,
+i.e. within ~1e-3 of the true fixed point: a solver that stops a few sweeps
+earlier or later differs by (sweeps x 1e-5).  The float64 path must agree to
+1e-10 with identical sweep counts.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 3e-4
+
+
+@pytest.fixture(scope='module')
+def ssn(built_library):
+    from tc_gan_b200 import clib, ssnode
+    if clib.libssnode.ssn_device_count() < 1:
+        pytest.fail('GPU tests need a CUDA device: the library has no CPU fallback')
+    return ssnode
+
+
+def seeded_problem(oracle, n_sites, nz, seed=0, jds=None, bandwidths=None, contrasts=(20.,)):
+    jds = jds or oracle.new_JDS()
+    rs = np.random.RandomState(seed)
+    zs = np.array([rs.rand(2 * n_sites, 2 * n_sites) for _ in range(nz)])
+    W = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], zs)
+    exts = oracle.stimulus_input(bandwidths if bandwidths is not None else oracle.DEFAULT_BANDWIDTHS,
+                                 n_sites, contrasts=contrasts)
+    return zs, W, exts
+
+
+@pytest.mark.parametrize('n_sites,io_type', [(51, 'asym_tanh'), (51, 'asym_linear'), (51, 'asym_power'),
+                                             (201, 'asym_tanh')])
+def test_golden_fixed_points(ssn, oracle, n_sites, io_type):
+    """Fixtures produced by the reference's own find_fixed_points (oracle/make_golden.py)."""
+    g = golden('fixed_points.npz')['R_%d_%s' % (n_sites, io_type)]
+    _, W, exts = seeded_problem(oracle, n_sites, len(g))
+    R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, io_type=io_type)
+    assert (err == 0).all()
+    np.testing.assert_allclose(R, g, rtol=RTOL, atol=ATOL)
+    Rp, errp, itsp = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, io_type=io_type, precise=True)
+    assert (errp == 0).all()
+    np.testing.assert_allclose(Rp, g, rtol=0, atol=1e-10)
+    _, _, it_ref = oracle.fixed_point_batch(W, exts, io_type=io_type, threads=4)
+    np.testing.assert_array_equal(itsp, it_ref)
+    assert np.abs(its - it_ref).max() <= 40
+
+
+@pytest.mark.parametrize('io_type', ['asym_linear', 'asym_power', 'asym_tanh'])
+def test_matlab_golden(ssn, io_type):
+    """tc_gan/tests/test_dynamics.py:76-126 through find_fixed_points(method='parallel')."""
+    g = golden('matlab_ne51.npz')
+    N = int(g['n_sites'])
+    (z,), (fps,), info = ssn.find_fixed_points(
+        1, iter([('dummy', g['W'])]), g['exts'], k=float(g['k']), n=float(g['n']),
+        r0=np.zeros(2 * N), io_type=io_type, method='parallel', check=True)
+    assert z == 'dummy' and info.rejections == 0 and info.unused == 0
+    center, ofs = N // 2, len(g['E_Tuning']) // 2
+    np.testing.assert_allclose(fps[:, center - ofs:center + ofs + 1].T, g['E_Tuning'], rtol=0.1)
+    np.testing.assert_allclose(fps, g['fp_' + io_type], rtol=RTOL, atol=ATOL)
+    assert all(s.success and s.message == 'Converged' for s in info.solutions[0])
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_fixed_point_c_abi_seeds(ssn, seed):
+    """tc_gan/tests/test_ssn.py:66-74 (atol=1e-10) through the reference ABI symbol."""
+    g = golden('ssn_seeds_atol1e-10.npz')['x']
+    kwargs = ssn.make_solver_params(seed=seed, io_type='asym_tanh')
+    kwargs.update(atol=1e-10, tau=(.016, .002))
+    sol = ssn.fixed_point(**kwargs)
+    assert sol.success and sol.message == 'Converged'
+    np.testing.assert_allclose(sol.x, g[seed], rtol=0, atol=1e-9)
+
+
+def test_divergence_codes(ssn):
+    """tc_gan/tests/test_dynamics.py:129-137 and the check=True exception."""
+    sol = ssn.fixed_point(W=[[2, 0], [0, 0]], ext=[10, 10], k=1, n=1, r0=[0, 0],
+                          max_iter=10000000, io_type='asym_linear')
+    assert sol.message == "Reached to rate_stop_at" and sol.error == 2 and not sol.success
+    sol = ssn.fixed_point(W=[[2, 0], [0, 0]], ext=[10, 10], k=1, n=1, r0=[0, 0], max_iter=50,
+                          io_type='asym_tanh')
+    assert sol.error == 1 and sol.message == "SSN Convergence Failed"
+    with pytest.raises(ssn.FixedPointError):
+        ssn.fixed_point(W=[[2, 0], [0, 0]], ext=[10, 10], k=1, n=1, max_iter=50, io_type='asym_tanh',
+                        check=True)
+    # Fortran-ordered input must be honoured (the reference silently transposes it)
+    W = np.asfortranarray(np.array([[0., 0.5], [0., 0.]]))
+    sol = ssn.fixed_point(W=W, ext=[1., 2.], k=1, n=1, io_type='asym_linear', atol=1e-12, max_iter=100000)
+    np.testing.assert_allclose(sol.x, [2., 2.], atol=1e-8)
+
+
+def test_status_codes_match_reference(ssn, oracle):
+    """asym_power + rate_stop_at=200 with the original J, D: a mix of 0 and 2."""
+    g = golden('failure_codes.npz')
+    nz = len(g['status_power'])
+    jds = dict(J=oracle.DEFAULT_J, D=oracle.DEFAULT_D, S=oracle.DEFAULT_S)
+    _, W, exts = seeded_problem(oracle, 51, nz, seed=3, jds=jds)
+    kw = dict(k=0.01, n=2.2, io_type='asym_power', rate_stop_at=200, max_iter=3000)
+    for precise in (False, True):
+        R, err, _ = ssn.fixed_points_batch(W, exts, precise=precise, **kw)
+        np.testing.assert_array_equal(err, g['status_power'])
+        ok = err == 0
+        np.testing.assert_allclose(R[ok], g['R_power'][ok], rtol=RTOL, atol=ATOL if not precise else 1e-9)
+    assert set(np.unique(g['status_power'])) == {0, 2}
+
+
+def test_find_fixed_points_rejection_bookkeeping(ssn, oracle):
+    """Kept networks = first `num` successes in generator order; counter keyed by the
+    error of the first failing stimulus when visited last to first (ssnode.py:390-420)."""
+    jds = dict(J=oracle.DEFAULT_J, D=oracle.DEFAULT_D, S=oracle.DEFAULT_S)
+    n_sites, num = 51, 6
+    exts = oracle.stimulus_input(oracle.DEFAULT_BANDWIDTHS, n_sites)
+    kw = dict(k=0.01, n=2.2, io_type='asym_power', rate_stop_at=200, max_iter=3000)
+
+    def gen(rs):
+        idx = 0
+        while True:
+            z = rs.rand(2 * n_sites, 2 * n_sites)
+            yield (idx, z), oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
+            idx += 1
+
+    rs = np.random.RandomState(3)
+    zs, Rs, info = ssn.find_fixed_points(num, gen(rs), exts, r0=np.zeros(2 * n_sites), **kw)
+    # serial emulation with the oracle
+    rs2 = np.random.RandomState(3)
+    kept, counter, consumed = [], {}, 0
+    for (idx, z), W in gen(rs2):
+        consumed += 1
+        R, st, _ = oracle.fixed_point_batch(W[None], exts, stop_at_first_failure=True,
+                                            io_type='asym_power', rate_stop_at=200, max_iter=3000)
+        bad = [b for b in range(len(exts) - 1, -1, -1) if st[0, b] > 0]
+        if bad:
+            counter[int(st[0, bad[0]])] = counter.get(int(st[0, bad[0]]), 0) + 1
+        else:
+            kept.append((idx, R[0]))
+        if len(kept) == num:
+            break
+    assert [i for i, _ in kept] == [int(z[0]) for z in zs]
+    assert dict(info.counter) == counter and info.rejections == sum(counter.values()) > 0
+    assert info.unused == 0
+    np.testing.assert_allclose(Rs, np.array([r for _, r in kept]), rtol=RTOL, atol=ATOL)
+    # the generator was consumed exactly as far as the serial finder would
+    assert rs.rand() == rs2.rand()
+    assert Rs.shape == (num, len(exts), 2 * n_sites) and len(info.solutions) == num
+
+
+@pytest.mark.parametrize('n_sites,nz,nb', [(1, 1, 1), (7, 3, 3), (10, 2, 11), (33, 5, 8), (101, 3, 9),
+                                           (128, 2, 2), (201, 2, 50)])
+def test_ragged_shapes(ssn, oracle, n_sites, nz, nb):
+    """Odd sizes, partial stimulus panels, several panels per network, every cluster width."""
+    bw = np.linspace(0, 1, nb) if nb > 1 else [0.5]
+    contrasts = (20.,) if nb != 50 else (5, 10, 20, 30, 40)
+    if nb == 50:
+        bw = np.linspace(0, 1, 10)
+    _, W, exts = seeded_problem(oracle, n_sites, nz, seed=n_sites + nb, bandwidths=bw, contrasts=contrasts)
+    assert len(exts) == nb
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+    R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2)
+    np.testing.assert_array_equal(err, st_o)
+    np.testing.assert_allclose(R, Ro, rtol=RTOL, atol=ATOL)
+    Rp, errp, itsp = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, precise=True)
+    np.testing.assert_array_equal(itsp, it_o)
+    np.testing.assert_allclose(Rp, Ro, rtol=0, atol=1e-10)
+
+
+def test_initial_state_and_max_iter(ssn, oracle):
+    n_sites = 20
+    _, W, exts = seeded_problem(oracle, n_sites, 2, seed=1)
+    r0 = np.full(2 * n_sites, 3.0)
+    for precise in (False, True):
+        R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, r0=r0, max_iter=25, precise=precise)
+        assert (err == 1).all() and (its == 25).all()
+        # 25 Euler sweeps from r0, float64
+        ref = np.empty_like(R)
+        for z in range(2):
+            for b in range(len(exts)):
+                x, code, it = oracle.fixed_point(W[z], exts[b], r0=r0, max_iter=25)
+                assert code == 1
+                ref[z, b] = x
+        np.testing.assert_allclose(R, ref, rtol=1e-5, atol=1e-5 if not precise else 1e-12)
+
+
+def test_from_z_device_path_and_weight_kernel(ssn, oracle):
+    """W built on chip from z (SSN_W_FROM_Z) equals W supplied densely; ssn_generate_weight
+    equals weight_gen.generate_weight."""
+    from tc_gan_b200 import clib
+    from tc_gan_b200.weight_gen import generate_weight_batch_gpu
+    n_sites, nz = 201, 3
+    jds = oracle.new_JDS()
+    zs, W, exts = seeded_problem(oracle, n_sites, nz, seed=2)
+    Wg = generate_weight_batch_gpu(n_sites, jds['J'], jds['D'], jds['S'], zs)
+    np.testing.assert_allclose(Wg, W, rtol=2e-6, atol=1e-7)
+    dim, nb = 2 * n_sites, len(exts)
+    z32 = np.ascontiguousarray(zs, np.float32)
+    e32 = np.ascontiguousarray(exts, np.float32)
+    R = np.empty((nz, nb, dim), np.float32)
+    st = np.empty((nz, nb), np.int32)
+    it = np.empty((nz, nb), np.int32)
+    sv = clib.make_solver(k=0.01, n=2.2)
+    clib.check_call(clib.libssnode.ssn_fixed_point_batch(
+        sv, nz, nb, n_sites, clib.W_FROM_Z, z32.ctypes.data, clib.make_jds(jds['J'], jds['D'], jds['S']),
+        e32.ctypes.data, 0, None, R.ctypes.data, st.ctypes.data, it.ctypes.data, 0, clib.MEM_HOST, None),
+        'ssn_fixed_point_batch')
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+    np.testing.assert_array_equal(st, st_o)
+    np.testing.assert_allclose(R, Ro, rtol=RTOL, atol=ATOL)
+
+
+def test_full_size_fixed_point_property(ssn, oracle):
+    """BASELINE config 2 at full size (1024 networks x 8 stimuli, 2N=402), through the
+    device-pointer C ABI: every solve converges and every returned state is a fixed point
+    of one further float64 Euler step to a few atol (size-independent property; the oracle
+    needs ~35 ms per solve, so it checks a sample)."""
+    import torch
+    from tc_gan_b200 import clib
+    n_sites, nz = 201, 1024
+    dim = 2 * n_sites
+    jds = oracle.new_JDS()
+    exts = oracle.stimulus_input(oracle.DEFAULT_BANDWIDTHS, n_sites)
+    nb = len(exts)
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    z = torch.rand((nz, dim, dim), generator=g, device=dev, dtype=torch.float32)
+    e = torch.tensor(exts, dtype=torch.float32, device=dev)
+    R = torch.empty((nz, nb, dim), dtype=torch.float32, device=dev)
+    st = torch.empty((nz, nb), dtype=torch.int32, device=dev)
+    it = torch.empty((nz, nb), dtype=torch.int32, device=dev)
+    sv = clib.make_solver(k=0.01, n=2.2)
+    clib.check_call(clib.libssnode.ssn_fixed_point_batch(
+        sv, nz, nb, n_sites, clib.W_FROM_Z, z.data_ptr(), clib.make_jds(jds['J'], jds['D'], jds['S']),
+        e.data_ptr(), 0, None, R.data_ptr(), st.data_ptr(), it.data_ptr(), 0, clib.MEM_DEVICE,
+        torch.cuda.current_stream().cuda_stream), 'ssn_fixed_point_batch')
+    torch.cuda.synchronize()
+    st, it = st.cpu().numpy(), it.cpu().numpy()
+    assert (st == 0).all() and it.min() > 50 and it.max() < 5000
+    sample = [0, 1, 511, 1023]
+    zs = z[sample].double().cpu().numpy()
+    W = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], zs)
+    Rs = R[sample].double().cpu().numpy()
+    eps = np.r_[np.full(n_sites, 8e-4 / 0.01589), np.full(n_sites, 8e-4 / 0.002)]
+    step = (oracle.io_fun(np.einsum('zij,zbj->zbi', W, Rs) + exts[None]) - Rs) * eps
+    assert np.abs(step).max() < 5e-5
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+    np.testing.assert_allclose(Rs, Ro, rtol=RTOL, atol=ATOL)
+    assert np.isfinite(R.cpu().numpy()).all()
