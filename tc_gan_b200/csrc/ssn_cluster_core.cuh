@@ -142,20 +142,35 @@ __device__ __forceinline__ void contract_panel(float (&acc)[TI][TB], const float
     }
 }
 
-// Reduce-scatter of the KL=8 partial tiles: on return out[t] is the full sum for
-// stimulus b = kl of row t.
-template <int TI>
-__device__ __forceinline__ void reduce_scatter8(const float (&acc)[TI][TB], float (&out)[TI], int kl) {
+// ---- ownership after the reduce-scatter ------------------------------------------------
+// The KL k-lanes of a row group hold partial sums of a TI x 8 tile.  After the
+// reduce-scatter, lane kl owns stimulus kl / (KL/8) and the rows
+// [sub*TO, sub*TO+TO) of the group, sub = kl % (KL/8), TO = ceil(TI / (KL/8)).
+template <int TI, int KL>
+struct Owner {
+    static constexpr int SPLIT = KL / TB;                  // lanes sharing one stimulus
+    static constexpr int TO = (TI + SPLIT - 1) / SPLIT;    // rows owned per lane
+    __device__ static __forceinline__ int stim(int kl) { return kl / SPLIT; }
+    __device__ static __forceinline__ int first_row(int kl) { return (kl % SPLIT) * TO; }
+};
+
+// Reduce-scatter of the KL partial tiles (KL = 8 or 16): on return out[u] is the full
+// sum for stimulus Owner::stim(kl), row Owner::first_row(kl) + u of the group.
+template <int TI, int KL>
+__device__ __forceinline__ void reduce_scatter(const float (&acc)[TI][TB],
+                                               float (&out)[Owner<TI, KL>::TO], int kl) {
+    static_assert(KL == 8 || KL == 16, "k-lanes");
     const unsigned full = 0xffffffffu;
-    float v4[TI][4], v2[TI][2];
-    const bool u4 = kl & 4, u2 = kl & 2, u1 = kl & 1;
+    constexpr int S = KL / TB;                 // 1 or 2
+    float v4[TI][4], v2[TI][2], v1[TI];
+    const bool u4 = kl & (4 * S), u2 = kl & (2 * S), u1 = kl & S;
 #pragma unroll
     for (int t = 0; t < TI; ++t)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const float send = u4 ? acc[t][c] : acc[t][4 + c];
             const float keep = u4 ? acc[t][4 + c] : acc[t][c];
-            v4[t][c] = keep + __shfl_xor_sync(full, send, 4);
+            v4[t][c] = keep + __shfl_xor_sync(full, send, 4 * S);
         }
 #pragma unroll
     for (int t = 0; t < TI; ++t)
@@ -163,23 +178,73 @@ __device__ __forceinline__ void reduce_scatter8(const float (&acc)[TI][TB], floa
         for (int c = 0; c < 2; ++c) {
             const float send = u2 ? v4[t][c] : v4[t][2 + c];
             const float keep = u2 ? v4[t][2 + c] : v4[t][c];
-            v2[t][c] = keep + __shfl_xor_sync(full, send, 2);
+            v2[t][c] = keep + __shfl_xor_sync(full, send, 2 * S);
         }
 #pragma unroll
     for (int t = 0; t < TI; ++t) {
         const float send = u1 ? v2[t][0] : v2[t][1];
         const float keep = u1 ? v2[t][1] : v2[t][0];
-        out[t] = keep + __shfl_xor_sync(full, send, 1);
+        v1[t] = keep + __shfl_xor_sync(full, send, S);
+    }
+    if (S == 1) {
+#pragma unroll
+        for (int u = 0; u < Owner<TI, KL>::TO; ++u) out[u] = v1[u < TI ? u : 0];
+    } else {
+        // two lanes hold partial sums of the same stimulus: split the rows between them
+        constexpr int TO = Owner<TI, KL>::TO;
+        const bool hi = kl & 1;
+#pragma unroll
+        for (int u = 0; u < TO; ++u) {
+            const float mine = hi ? (TO + u < TI ? v1[TO + u < TI ? TO + u : 0] : 0.f) : v1[u];
+            const float theirs = hi ? v1[u] : (TO + u < TI ? v1[TO + u < TI ? TO + u : 0] : 0.f);
+            out[u] = mine + __shfl_xor_sync(full, theirs, 1);
+        }
     }
 }
 
-// OR of a per-thread predicate over the lanes that share kl (stimulus), as a
-// bit mask indexed by stimulus.
+// OR of a per-thread predicate over the lanes that own the same stimulus, as a bit
+// mask indexed by stimulus (lane l owns stimulus (l % KL) / (KL/8)).
+template <int KL>
 __device__ __forceinline__ unsigned stim_mask(bool pred) {
     unsigned m = __ballot_sync(0xffffffffu, pred);
-    m |= m >> 16;
-    m |= m >> 8;
-    return m & 0xffu;
+    if (KL == 8) {
+        m |= m >> 16;
+        m |= m >> 8;
+        return m & 0xffu;
+    }
+    m |= m >> 16;                 // fold the two row groups of the warp
+    m &= 0xffffu;
+    m |= m >> 1;                  // fold the two lanes of a stimulus: bits 0,2,4,..
+    unsigned r = 0;
+#pragma unroll
+    for (int b = 0; b < TB; ++b) r |= ((m >> (2 * b)) & 1u) << b;
+    return r;
+}
+
+// ---- distributed shared memory helpers (32-bit shared::cluster addresses) ----------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ unsigned map_to_rank(unsigned smem_addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(unsigned addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(unsigned addr, unsigned v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// fast float transfer function: MUFU-based pow / tanh (relative error ~4e-7), used where
+// the float64 reference expansion does not apply
+__device__ __forceinline__ float io_eval_fast(const IoConst<float> &c, float v) {
+    if (v <= 0.f) return 0.f;
+    if (c.io_type == SSN_IO_POWER || v <= c.v0) return c.k * exp2f(c.n * __log2f(v));
+    if (c.io_type == SSN_IO_LINEAR) return fmaf(c.lin_slope, v - c.v0, c.r_soft);
+    const float e = __expf(2.f * c.tanh_scale * (v - c.v0));        // tanh(x) = 1 - 2/(e^{2x}+1)
+    return fmaf(c.span, 1.f - __fdividef(2.f, e + 1.f), c.r_soft);
 }
 
 }  // namespace ssn

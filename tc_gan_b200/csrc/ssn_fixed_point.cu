@@ -37,7 +37,8 @@ struct FpArgs {
 
 template <int TI, int KL, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_fp_cluster_kernel(const FpArgs a) {
-    static_assert(KL == 8, "reduce_scatter8 assumes 8 k-lanes");
+    using Own = Owner<TI, KL>;
+    constexpr int TO = Own::TO;
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -56,23 +57,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_fp_cluster_kernel(const Fp
     const int warp = tid >> 5, lane = tid & 31;
     const int kl = lane % KL;
     const int grp = warp * (32 / KL) + lane / KL;
-    const int row0 = grp * TI;                               // first local row of this thread
     const int row_base = rank * rpc;
     const int rows_here = max(0, min(rpc, dim - row_base));
 
-    int wrow[TI];
-    bool valid[TI];
+    int wrow[TI];                                            // smem rows this thread contracts
 #pragma unroll
-    for (int t = 0; t < TI; ++t) {
-        valid[t] = row0 + t < rows_here;
-        wrow[t] = min(row0 + t, rows_here - 1);
-    }
+    for (int t = 0; t < TI; ++t) wrow[t] = min(grp * TI + t, rows_here - 1);
 
-    // peers' panels / misc blocks through distributed shared memory
-    float *Xpeer[MAX_CLUSTER];
+    // rows / stimulus this thread owns after the reduce-scatter
+    const int my_stim = Own::stim(kl);
+    const int own0 = grp * TI + Own::first_row(kl);          // first owned local row
+    bool valid[TO];
 #pragma unroll
-    for (int p = 0; p < MAX_CLUSTER; ++p)
-        Xpeer[p] = p < csize ? cluster.map_shared_rank(Xf, p) : Xf;
+    for (int u = 0; u < TO; ++u)
+        valid[u] = (Own::first_row(kl) + u < TI) && (own0 + u < rows_here);
+
+    // peers' panels and flag words through distributed shared memory
+    unsigned xpeer[MAX_CLUSTER];
+#pragma unroll
+    for (int p = 0; p < MAX_CLUSTER; ++p) xpeer[p] = map_to_rank(smem_u32(Xf), p < csize ? p : 0);
 
     if (a.w_kind == SSN_W_FROM_Z) build_profile_table(a.wc, a.n_sites, gtab, tid, nthreads);
     for (int i = tid; i < 2 * 2 * P * 4; i += nthreads) Xf[i] = 0.f;     // padding columns stay 0
@@ -80,12 +83,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_fp_cluster_kernel(const Fp
     __syncthreads();
 
     const int n_chunks = (a.nb + TB - 1) / TB;
+    const float atol_f = (float)a.atol;
+    (void)atol_f;
 
     for (;;) {
         // ---- next network from the global queue ----
         if (rank == 0 && tid == 0) {
             const int n = atomicAdd(a.work_counter, 1);
-            for (int p = 0; p < csize; ++p) cluster.map_shared_rank(&misc->next_net, p)[0] = n;
+            for (int p = 0; p < csize; ++p) st_cluster_u32(map_to_rank(smem_u32(&misc->next_net), p), (unsigned)n);
         }
         cluster.sync();
         const int net = misc->next_net;
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_fp_cluster_kernel(const Fp
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
             const int b0 = chunk * TB;
             const int nact = min(TB, a.nb - b0);
-            const bool active = kl < nact;
+            const bool active = my_stim < nact;
             const float *ext_net = a.ext + (size_t)net * a.ext_stride_z;
 
             // stimulus rows of this CTA -> smem, [local row][8]
@@ -107,63 +112,72 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_fp_cluster_kernel(const Fp
             }
 
             // initial state (float64 master copy in registers), published to every CTA
-            double rstate[TI];
+            double rstate[TO];
+            float ext_own[TO];
+            double eps_own[TO];
+            unsigned xoff[TO];                                // byte offset of (row, stim) in panel 0
 #pragma unroll
-            for (int t = 0; t < TI; ++t) {
-                rstate[t] = 0.0;
-                if (valid[t] && active && a.r_init)
-                    rstate[t] = (double)__ldg(a.r_init + ((size_t)net * a.nb + b0 + kl) * dim + row_base + row0 + t);
-                if (valid[t]) {
-                    const int idx = panel_index(P, 0, row_base + row0 + t, kl);
-                    const float rf = (float)rstate[t];
+            for (int u = 0; u < TO; ++u) {
+                rstate[u] = 0.0;
+                ext_own[u] = 0.f;
+                eps_own[u] = 0.0;
+                xoff[u] = 0u;
+                if (valid[u]) {
+                    const int gr = row_base + own0 + u;
+                    if (active && a.r_init)
+                        rstate[u] = (double)__ldg(a.r_init + ((size_t)net * a.nb + b0 + my_stim) * dim + gr);
+                    eps_own[u] = gr < a.n_sites ? a.eps_E : a.eps_I;
+                    xoff[u] = 4u * (unsigned)panel_index(P, 0, gr, my_stim);
+                    const float rf = (float)rstate[u];
 #pragma unroll
                     for (int p = 0; p < MAX_CLUSTER; ++p)
-                        if (p < csize) Xpeer[p][idx] = rf;
+                        if (p < csize) st_cluster_f32(xpeer[p] + xoff[u], rf);
                 }
             }
             cluster.sync();
+#pragma unroll
+            for (int u = 0; u < TO; ++u)
+                if (valid[u]) ext_own[u] = extsm[(own0 + u) * TB + my_stim];
 
             unsigned done = nact >= TB ? 0u : (0xffu << nact) & 0xffu;   // finished stimuli
-            int my_status = 1, my_iters = a.max_iter;                   // of stimulus kl
+            int my_status = 1, my_iters = a.max_iter;                   // of stimulus my_stim
             int buf = 0;
+            const unsigned buf_bytes = 2u * (unsigned)P * 16u;           // one panel buffer (2 planes)
 
             for (int it = 1; it <= a.max_iter; ++it) {
-                float acc[TI][TB], v[TI];
+                float acc[TI][TB], v[TO];
                 contract_panel<TI, KL>(acc, Wsm, X4, P, kpad, buf, wrow, kl);
-                reduce_scatter8<TI>(acc, v, kl);
+                reduce_scatter<TI, KL>(acc, v, kl);
 
                 const int nbuf = buf ^ 1;
-                const bool frozen = (done >> kl) & 1u;
+                const bool frozen = (done >> my_stim) & 1u;
                 bool moving = false, above = false;
 #pragma unroll
-                for (int t = 0; t < TI; ++t) {
-                    if (valid[t]) {
-                        const int lr = row0 + t;
-                        const float vt = v[t] + extsm[lr * TB + kl];
-                        const float fv = io_eval<float>(a.io, vt);
-                        const double eps = (row_base + lr) < a.n_sites ? a.eps_E : a.eps_I;
-                        const double r_old = rstate[t];
-                        const double r_new = r_old + ((double)fv - r_old) * eps;
+                for (int u = 0; u < TO; ++u) {
+                    if (valid[u]) {
+                        const float fv = io_eval<float>(a.io, v[u] + ext_own[u]);
+                        const double r_old = rstate[u];
+                        const double r_new = r_old + ((double)fv - r_old) * eps_own[u];
                         if (!frozen) {
                             moving |= fabs(r_new - r_old) >= a.atol;
                             above |= r_new >= a.r_hard;
-                            rstate[t] = r_new;
+                            rstate[u] = r_new;
                         }
-                        const int idx = panel_index(P, nbuf, row_base + lr, kl);
-                        const float rf = (float)rstate[t];
+                        const float rf = (float)rstate[u];
+                        const unsigned off = xoff[u] + (nbuf ? buf_bytes : 0u);
 #pragma unroll
                         for (int p = 0; p < MAX_CLUSTER; ++p)
-                            if (p < csize) Xpeer[p][idx] = rf;
+                            if (p < csize) st_cluster_f32(xpeer[p] + off, rf);
                     }
                 }
-                const unsigned mm = stim_mask(moving), ma = stim_mask(above);
+                const unsigned mm = stim_mask<KL>(moving), ma = stim_mask<KL>(above);
                 if (lane == 0 && (mm | ma)) atomicOr(&misc->myflags, mm | (ma << 8));
                 __syncthreads();
                 if (tid == 0) {
                     const unsigned f = misc->myflags;
                     misc->myflags = 0u;
                     for (int p = 0; p < csize; ++p)
-                        cluster.map_shared_rank(&misc->flags[nbuf][rank], p)[0] = f;
+                        st_cluster_u32(map_to_rank(smem_u32(&misc->flags[nbuf][rank]), p), f);
                 }
                 cluster.sync();
                 unsigned F = 0u;
@@ -172,8 +186,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_fp_cluster_kernel(const Fp
                 // reference order: convergence first, then the hard bound (ssnode.c:84-102)
                 const unsigned conv_now = ~moving_all & ~done & 0xffu;
                 const unsigned hard_now = a.check_hard ? (above_all & ~done & ~conv_now & 0xffu) : 0u;
-                if ((conv_now >> kl) & 1u) { my_status = 0; my_iters = it; }
-                if ((hard_now >> kl) & 1u) { my_status = 2; my_iters = it; }
+                if ((conv_now >> my_stim) & 1u) { my_status = 0; my_iters = it; }
+                if ((hard_now >> my_stim) & 1u) { my_status = 2; my_iters = it; }
                 done |= conv_now | hard_now;
                 buf = nbuf;
                 if (done == 0xffu) break;
@@ -181,12 +195,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_fp_cluster_kernel(const Fp
 
             // ---- results ----
 #pragma unroll
-            for (int t = 0; t < TI; ++t)
-                if (valid[t] && active)
-                    a.R[((size_t)net * a.nb + b0 + kl) * dim + row_base + row0 + t] = (float)rstate[t];
-            if (rank == 0 && tid < TB && tid < nact) {          // warp 0, group 0: lane == kl
-                a.status[(size_t)net * a.nb + b0 + tid] = my_status;
-                if (a.iters) a.iters[(size_t)net * a.nb + b0 + tid] = my_iters;
+            for (int u = 0; u < TO; ++u)
+                if (valid[u] && active)
+                    a.R[((size_t)net * a.nb + b0 + my_stim) * dim + row_base + own0 + u] = (float)rstate[u];
+            // warp 0, first row group: one lane per stimulus (the lane with sub-index 0)
+            if (rank == 0 && tid < KL && (kl % Own::SPLIT) == 0 && active) {
+                a.status[(size_t)net * a.nb + b0 + my_stim] = my_status;
+                if (a.iters) a.iters[(size_t)net * a.nb + b0 + my_stim] = my_iters;
             }
             // every CTA must be out of the sweep loop before the panel is re-initialised
             cluster.sync();
@@ -341,42 +356,48 @@ static int max_optin_smem() {
     return v;
 }
 
-// Smallest cluster whose CTAs can hold their slice of the matrix.
-bool choose_cluster_shape(int n_sites, ClusterShape *out, int smem_limit) {
+typedef void (*FpKernel)(const FpArgs);
+struct FpVariant { FpKernel fn; int threads; int rows; int kl; };
+
+// rows covered = (32/KL) * NWARPS * TI; kpad must be a multiple of 4*KL
+static const FpVariant kFpVariants[] = {
+    {ssn_fp_cluster_kernel<4, 16, 8>, 256, 64, 16},
+    {ssn_fp_cluster_kernel<7, 16, 8>, 256, 112, 16},
+    {ssn_fp_cluster_kernel<7, 8, 8>, 256, 224, 8},
+};
+
+// Smallest cluster whose CTAs can hold their slice of the matrix, and the kernel
+// instantiation that covers its rows.
+bool choose_cluster_shape(int n_sites, ClusterShape *out, int smem_limit, int *variant) {
     const int dim = 2 * n_sites;
     ClusterShape s;
     s.dim = dim;
-    s.kpad = ((dim + 31) / 32) * 32;
     for (int c = 1; c <= MAX_CLUSTER; c *= 2) {
         s.csize = c;
         s.rpc = (dim + c - 1) / c;
         if (s.rpc * (c - 1) >= dim) continue;               // a CTA would own no rows
-        if (s.rpc > 32 * 7) continue;                       // widest instantiation: 8 warps x 4 groups x 7 rows
-        if (smem_layout(s, n_sites).total <= smem_limit) { *out = s; return true; }
+        for (int v = 0; v < 3; ++v) {
+            if (kFpVariants[v].rows < s.rpc) continue;
+            const int q = 4 * kFpVariants[v].kl;
+            s.kpad = ((dim + q - 1) / q) * q;
+            if (smem_layout(s, n_sites).total <= smem_limit) { *out = s; *variant = v; return true; }
+            break;
+        }
     }
     return false;
-}
-
-typedef void (*FpKernel)(const FpArgs);
-struct FpVariant { FpKernel fn; int threads; int rows; };
-
-static FpVariant pick_fp_variant(int rpc) {
-    // rows covered = (32/KL) * NWARPS * TI
-    if (rpc <= 16 * 4) return {ssn_fp_cluster_kernel<4, 8, 4>, 128, 64};
-    if (rpc <= 16 * 7) return {ssn_fp_cluster_kernel<7, 8, 4>, 128, 112};
-    return {ssn_fp_cluster_kernel<7, 8, 8>, 256, 224};
 }
 
 struct FpLaunchPlan { FpVariant var; ClusterShape shape; int smem; int clusters; };
 
 static int plan_fixed_point(int n_sites, int nz, FpLaunchPlan *plan) {
     const int limit = max_optin_smem();
-    if (!choose_cluster_shape(n_sites, &plan->shape, limit)) {
+    int variant = 0;
+    if (!choose_cluster_shape(n_sites, &plan->shape, limit, &variant)) {
         set_error("fixed-point kernel: 2N=%d does not fit a cluster of %d CTAs (smem %d B)",
                   2 * n_sites, MAX_CLUSTER, limit);
         return -1;
     }
-    plan->var = pick_fp_variant(plan->shape.rpc);
+    plan->var = kFpVariants[variant];
     plan->smem = smem_layout(plan->shape, n_sites).total;
     SSN_CUDA(cudaFuncSetAttribute(plan->var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem));
     cudaLaunchConfig_t cfg = {};

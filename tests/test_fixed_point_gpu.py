@@ -124,7 +124,7 @@ def test_find_fixed_points_rejection_bookkeeping(ssn, oracle):
         idx = 0
         while True:
             z = rs.rand(2 * n_sites, 2 * n_sites)
-            yield (idx, z), oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
+            yield z, oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
             idx += 1
 
     rs = np.random.RandomState(3)
@@ -132,7 +132,7 @@ def test_find_fixed_points_rejection_bookkeeping(ssn, oracle):
     # serial emulation with the oracle
     rs2 = np.random.RandomState(3)
     kept, counter, consumed = [], {}, 0
-    for (idx, z), W in gen(rs2):
+    for z, W in gen(rs2):
         consumed += 1
         R, st, _ = oracle.fixed_point_batch(W[None], exts, stop_at_first_failure=True,
                                             io_type='asym_power', rate_stop_at=200, max_iter=3000)
@@ -140,10 +140,10 @@ def test_find_fixed_points_rejection_bookkeeping(ssn, oracle):
         if bad:
             counter[int(st[0, bad[0]])] = counter.get(int(st[0, bad[0]]), 0) + 1
         else:
-            kept.append((idx, R[0]))
+            kept.append((z, R[0]))
         if len(kept) == num:
             break
-    assert [i for i, _ in kept] == [int(z[0]) for z in zs]
+    np.testing.assert_array_equal(np.array([zz for zz, _ in kept]), zs)
     assert dict(info.counter) == counter and info.rejections == sum(counter.values()) > 0
     assert info.unused == 0
     np.testing.assert_allclose(Rs, np.array([r for _, r in kept]), rtol=RTOL, atol=ATOL)
