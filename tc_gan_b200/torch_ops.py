@@ -1,0 +1,215 @@
+"""
+PyTorch-facing operators over libssnode.so (device pointers through the C ABI).
+
+These replace the Theano ops of the reference on the SSN path:
+
+* `fixed_points` / `SSNFixedPoint`  -- batched fixed points of W(z; J, D, S) with the
+  implicit-function-theorem gradient w.r.t. (J, D, S) in backward
+  (tc_gan/ssnode.py:332-510 + gradient_expressions/SS_grad.py:17-76 +
+  make_w_batch.py:36-121 + run/gan.py:902-911).
+* `euler_ssn` / `EulerSSN` -- fixed-length unrolled Euler dynamics with
+  time-average / dynamics-penalty / rate-penalty outputs and BPTT in backward
+  (tc_gan/networks/ssn.py:555-576, 598-633).
+
+torch is used for device memory, streams and autograd bookkeeping only; all
+arithmetic on the path is in the CUDA library.  CPU tensors are rejected.
+"""
+import torch
+
+from . import clib
+from .clib import libssnode
+
+
+def _jds_struct(J, D, S):
+    return clib.make_jds(J.detach().double().cpu().numpy(), D.detach().double().cpu().numpy(),
+                         S.detach().double().cpu().numpy())
+
+
+def _check_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise clib.SSNLibraryError('tc_gan_b200.torch_ops needs CUDA tensors (there is no CPU fallback)')
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_solver(**kw):
+    """Solver knobs with the defaults of tc_gan.ssnode.fixed_point (ssnode.py:159-165)."""
+    return clib.make_solver(**kw)
+
+
+def fixed_points(z, J, D, S, ext, solver=None, r_init=None, precise=False):
+    """
+    Fixed points of the networks W(z; J, D, S) for every stimulus.
+
+    z [nz, 2N, 2N] float32 CUDA, ext [nb, 2N] or [nz, nb, 2N]; returns
+    (R [nz, nb, 2N] float32, status [nz, nb] int32, iters [nz, nb] int32) with the
+    reference's error codes (0 converged, 1 max_iter / non-finite, 2 rate_stop_at).
+    """
+    _check_cuda(z, ext, r_init)
+    solver = solver or make_solver()
+    z32, e32 = _f32c(z), _f32c(ext)
+    nz, dim = z32.shape[0], z32.shape[1]
+    nb = e32.shape[-2]
+    R = torch.empty((nz, nb, dim), dtype=torch.float32, device=z.device)
+    status = torch.empty((nz, nb), dtype=torch.int32, device=z.device)
+    iters = torch.empty((nz, nb), dtype=torch.int32, device=z.device)
+    r0 = _f32c(r_init) if r_init is not None else None
+    with torch.cuda.device(z.device):
+        clib.check_call(libssnode.ssn_fixed_point_batch(
+            solver, nz, nb, dim // 2, clib.W_FROM_Z, z32.data_ptr(), _jds_struct(J, D, S), e32.data_ptr(),
+            int(e32.dim() == 3), None if r0 is None else r0.data_ptr(), R.data_ptr(), status.data_ptr(),
+            iters.data_ptr(), int(bool(precise)), clib.MEM_DEVICE, _stream()), 'ssn_fixed_point_batch')
+    return R, status, iters
+
+
+def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-6, return_mu=False):
+    """dL/d(J, D, S) (three float64 [2, 2] CUDA tensors) from dL/dR at the fixed points R."""
+    _check_cuda(z, ext, R, grad_R)
+    solver = solver or make_solver()
+    z32, e32, R32, g32 = _f32c(z), _f32c(ext), _f32c(R), _f32c(grad_R)
+    nz, dim = z32.shape[0], z32.shape[1]
+    nb = R32.shape[1]
+    grad = torch.empty(12, dtype=torch.float64, device=z.device)
+    mu = torch.empty_like(R32) if return_mu else None
+    status = torch.empty((nz, nb), dtype=torch.int32, device=z.device)
+    iters = torch.empty((nz, nb), dtype=torch.int32, device=z.device)
+    with torch.cuda.device(z.device):
+        clib.check_call(libssnode.ssn_ift_gradient_batch(
+            solver, nz, nb, dim // 2, z32.data_ptr(), _jds_struct(J, D, S), e32.data_ptr(), int(e32.dim() == 3),
+            R32.data_ptr(), g32.data_ptr(), float(rtol), grad.data_ptr(), None if mu is None else mu.data_ptr(),
+            status.data_ptr(), iters.data_ptr(), clib.MEM_DEVICE, _stream()), 'ssn_ift_gradient_batch')
+    dJ, dD, dS = grad[0:4].reshape(2, 2), grad[4:8].reshape(2, 2), grad[8:12].reshape(2, 2)
+    if return_mu:
+        return dJ, dD, dS, mu, status, iters
+    return dJ, dD, dS
+
+
+class SSNFixedPoint(torch.autograd.Function):
+    """R = fixed_point(W(z; J, D, S), ext); backward = implicit gradient w.r.t. J, D, S."""
+
+    @staticmethod
+    def forward(ctx, z, J, D, S, ext, solver, precise):
+        R, status, iters = fixed_points(z, J, D, S, ext, solver=solver, precise=precise)
+        ctx.save_for_backward(z, J, D, S, ext, R)
+        ctx.solver = solver
+        ctx.mark_non_differentiable(status, iters)
+        return R, status, iters
+
+    @staticmethod
+    def backward(ctx, grad_R, _gs, _gi):
+        z, J, D, S, ext, R = ctx.saved_tensors
+        dJ, dD, dS = ift_gradient(z, J, D, S, ext, R, grad_R, solver=ctx.solver)
+        return (None, dJ.to(J.dtype).to(J.device), dD.to(D.dtype).to(D.device), dS.to(S.dtype).to(S.device),
+                None, None, None)
+
+
+def ssn_fixed_point(z, J, D, S, ext, solver=None, precise=False):
+    """Differentiable (w.r.t. J, D, S) batched fixed-point solve; returns (R, status, iters)."""
+    return SSNFixedPoint.apply(z, J, D, S, ext, solver or make_solver(), precise)
+
+
+# ---- unrolled Euler dynamics ------------------------------------------------------------
+
+def euler_forward(z, J, D, S, ext, seqlen, skip_steps, solver, rate_penalty_threshold=200.0,
+                  store=True):
+    _check_cuda(z, ext)
+    z32, e32 = _f32c(z), _f32c(ext)
+    nz, dim = z32.shape[0], z32.shape[1]
+    nb = e32.shape[-2]
+    dev = z.device
+    time_avg = torch.empty((nz, nb, dim), dtype=torch.float32, device=dev)
+    pen = torch.zeros(2, dtype=torch.float64, device=dev)
+    traj = torch.empty((nz, seqlen, nb, dim), dtype=torch.float32, device=dev) if store else None
+    gain = torch.empty((nz, seqlen, nb, dim), dtype=torch.float32, device=dev) if store else None
+    with torch.cuda.device(dev):
+        clib.check_call(libssnode.ssn_euler_forward(
+            solver, nz, nb, dim // 2, z32.data_ptr(), _jds_struct(J, D, S), e32.data_ptr(), int(e32.dim() == 3),
+            int(seqlen), int(skip_steps), float(rate_penalty_threshold), time_avg.data_ptr(), pen.data_ptr(),
+            None if traj is None else traj.data_ptr(), None if gain is None else gain.data_ptr(), _stream()),
+            'ssn_euler_forward')
+    return time_avg, pen, traj, gain
+
+
+class EulerSSN(torch.autograd.Function):
+    """(time_avg, dynamics_penalty, rate_penalty) of the unrolled Euler SSN; BPTT backward."""
+
+    @staticmethod
+    def forward(ctx, z, J, D, S, ext, seqlen, skip_steps, solver, threshold):
+        need_grad = any(ctx.needs_input_grad[1:4])
+        time_avg, pen, traj, gain = euler_forward(z, J, D, S, ext, seqlen, skip_steps, solver, threshold,
+                                                  store=need_grad)
+        nz, nb, dim = time_avg.shape
+        T = seqlen - skip_steps
+        n_dyn = max(nz * (T - 1) * nb * dim, 1)
+        n_rate = nz * T * nb * dim
+        dyn = (pen[0] / n_dyn).to(torch.float32)
+        rate = (pen[1] / n_rate).to(torch.float32)
+        ctx.save_for_backward(z, J, D, S, traj, gain)
+        ctx.meta = (seqlen, skip_steps, solver, threshold, n_dyn, n_rate)
+        return time_avg, dyn, rate
+
+    @staticmethod
+    def backward(ctx, g_avg, g_dyn, g_rate):
+        z, J, D, S, traj, gain = ctx.saved_tensors
+        seqlen, skip_steps, solver, threshold, n_dyn, n_rate = ctx.meta
+        nz, _, nb, dim = traj.shape
+        dev = traj.device
+        g32 = _f32c(g_avg) if g_avg is not None else torch.zeros((nz, nb, dim), dtype=torch.float32, device=dev)
+        w_dyn = float(g_dyn) / n_dyn if g_dyn is not None else 0.0
+        w_rate = float(g_rate) / n_rate if g_rate is not None else 0.0
+        adj = torch.empty_like(traj)
+        grad = torch.empty(12, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            clib.check_call(libssnode.ssn_euler_backward(
+                solver, nz, nb, dim // 2, _f32c(z).data_ptr(), _jds_struct(J, D, S), int(seqlen), int(skip_steps),
+                float(threshold), g32.data_ptr(), w_dyn, w_rate, traj.data_ptr(), gain.data_ptr(), adj.data_ptr(),
+                grad.data_ptr(), _stream()), 'ssn_euler_backward')
+        dJ, dD, dS = grad[0:4].reshape(2, 2), grad[4:8].reshape(2, 2), grad[8:12].reshape(2, 2)
+        return (None, dJ.to(J.dtype).to(J.device), dD.to(D.dtype).to(D.device), dS.to(S.dtype).to(S.device),
+                None, None, None, None, None)
+
+
+def euler_ssn(z, J, D, S, ext, seqlen=1200, skip_steps=1000, dt=0.1, tau_E=10.0, tau_I=1.0,
+              io_type='asym_tanh', k=0.01, n=2.2, rate_soft_bound=200., rate_hard_bound=1000.,
+              rate_penalty_threshold=200.0):
+    """
+    Unrolled Euler SSN as tc_gan.networks.ssn.EulerSSNModel: r_0 = 0,
+    r_{t+1} = (1 - dt/tau) r_t + dt/tau f(W r_t + I); returns
+    (time_avg [nz, nb, 2N], dynamics_penalty, rate_penalty), differentiable w.r.t. J, D, S.
+    Defaults are those of tc_gan/networks/wgan.py:39-63.
+    """
+    solver = clib.make_solver(io_type=io_type, k=k, n=n, tau=(tau_E, tau_I), dt=dt,
+                              rate_soft_bound=rate_soft_bound, rate_hard_bound=rate_hard_bound,
+                              rate_stop_at=rate_hard_bound)
+    return EulerSSN.apply(z, J, D, S, ext, int(seqlen), int(skip_steps), solver, float(rate_penalty_threshold))
+
+
+def smoke(oracle):
+    """Tiny forward + backward of both generator paths on cuda:0, checked against the oracle."""
+    import numpy as np
+    dev = torch.device('cuda:0')
+    n_sites, nz = 12, 2
+    jds = oracle.new_JDS()
+    exts = oracle.stimulus_input([0.125, 0.5, 1.0], n_sites)
+    rs = np.random.RandomState(5)
+    z = rs.rand(nz, 2 * n_sites, 2 * n_sites)
+    gR = rs.randn(nz, len(exts), 2 * n_sites)
+    W = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
+    Ro, st, _ = oracle.fixed_point_batch(W, exts)
+    t = lambda a, dt=torch.float32: torch.tensor(np.asarray(a), dtype=dt, device=dev)
+    J, D, S = (t(jds[k], torch.float64).requires_grad_() for k in 'JDS')
+    R, status, iters = ssn_fixed_point(t(z), J, D, S, t(exts))
+    assert (status == 0).all()
+    np.testing.assert_allclose(R.detach().cpu().numpy(), Ro, rtol=1e-4, atol=3e-4)
+    (R * t(gR)).sum().backward()
+    dJ, dD, dS, _ = oracle.ift_param_gradient(R.detach().double().cpu().numpy(), W, z, exts,
+                                               jds['J'], jds['D'], jds['S'], gR)
+    for got, want in ((J.grad, dJ), (D.grad, dD), (S.grad, dS)):
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-3, atol=1e-3 * np.abs(want).max())

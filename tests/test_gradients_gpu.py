@@ -1,0 +1,78 @@
+"""
+GPU parity tests of the generator gradients through the fixed point (K2) and through the
+unrolled Euler dynamics (K3/K4).  The reference's tests leave gradients unpinned (they only
+print them, tc_gan/tests/test_dynamics.py:140-276); the oracle's restatements are pinned by
+finite differences / torch float64 autograd in tests/test_oracle.py.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(built_library):
+    import torch
+    from tc_gan_b200 import clib, torch_ops
+    if clib.libssnode.ssn_device_count() < 1 or not torch.cuda.is_available():
+        pytest.fail('GPU tests need a CUDA device: the library has no CPU fallback')
+    return torch_ops
+
+
+def tens(a, dtype=None, grad=False):
+    import torch
+    t = torch.tensor(np.asarray(a), dtype=dtype or torch.float32, device='cuda:0')
+    return t.requires_grad_() if grad else t
+
+
+@pytest.mark.parametrize('n_sites,nz,nb,io_type', [(12, 2, 3, 'asym_tanh'), (51, 3, 8, 'asym_tanh'),
+                                                   (51, 2, 8, 'asym_power'), (40, 2, 11, 'asym_linear'),
+                                                   (201, 2, 8, 'asym_tanh')])
+def test_ift_gradient_matches_oracle(ops, oracle, n_sites, nz, nb, io_type):
+    """Same R and dL/dR into the CUDA adjoint path and the float64 restatement of
+    SS_grad.WRgrad_batch + make_w_batch + run/gan.py:902-911."""
+    import torch
+    jds = oracle.new_JDS()
+    bw = oracle.DEFAULT_BANDWIDTHS if nb == 8 else np.linspace(0.05, 1, nb)
+    exts = oracle.stimulus_input(bw, n_sites)
+    rs = np.random.RandomState(n_sites + nb)
+    z = rs.rand(nz, 2 * n_sites, 2 * n_sites).astype(np.float32).astype(np.float64)
+    W = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
+    R, st, _ = oracle.fixed_point_batch(W, exts, io_type=io_type, threads=8)
+    assert (st == 0).all()
+    R = R.astype(np.float32).astype(np.float64)
+    gR = rs.randn(nz, nb, 2 * n_sites).astype(np.float32).astype(np.float64)
+    dJ, dD, dS, mu = oracle.ift_param_gradient(R, W, z, exts, jds['J'], jds['D'], jds['S'], gR, io_type=io_type)
+    solver = ops.make_solver(io_type=io_type)
+    J, D, S = (tens(jds[k], torch.float64) for k in 'JDS')
+    gJ, gD, gS, mu_gpu, status, iters = ops.ift_gradient(tens(z), J, D, S, tens(exts), tens(R), tens(gR),
+                                                         solver=solver, return_mu=True)
+    assert (status.cpu().numpy() == 0).all()
+    np.testing.assert_allclose(mu_gpu.cpu().numpy(), mu, rtol=1e-3, atol=1e-3 * np.abs(mu).max())
+    for got, want in ((gJ, dJ), (gD, dD), (gS, dS)):
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+
+
+def test_fixed_point_autograd_function(ops, oracle):
+    """loss = <R, G> through SSNFixedPoint.apply; J.grad etc. against the oracle, and the
+    zero-gradient / ragged-panel edge cases."""
+    import torch
+    n_sites, nz = 30, 5
+    jds = oracle.new_JDS()
+    exts = oracle.stimulus_input(np.linspace(0, 1, 9), n_sites)
+    rs = np.random.RandomState(2)
+    z = rs.rand(nz, 2 * n_sites, 2 * n_sites).astype(np.float32).astype(np.float64)
+    G = rs.randn(nz, len(exts), 2 * n_sites)
+    G[1] = 0.0                                   # a network whose loss gradient vanishes
+    J, D, S = (tens(jds[k], torch.float64, grad=True) for k in 'JDS')
+    R, status, iters = ops.ssn_fixed_point(tens(z), J, D, S, tens(exts))
+    assert (status == 0).all() and not status.requires_grad
+    (R * tens(G)).sum().backward()
+    W = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
+    dJ, dD, dS, _ = oracle.ift_param_gradient(R.detach().double().cpu().numpy(), W, z, exts,
+                                               jds['J'], jds['D'], jds['S'], G)
+    for got, want in ((J.grad, dJ), (D.grad, dD), (S.grad, dS)):
+        assert got.shape == (2, 2) and got.dtype == torch.float64
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+    with pytest.raises(Exception):
+        ops.fixed_points(tens(z).cpu(), J, D, S, tens(exts).cpu())
