@@ -1,15 +1,410 @@
-// K3/K4 placeholder (implemented next).
+// K3 / K4: fixed-length unrolled Euler dynamics of the SSN and BPTT through it.
+//
+// Replaces the Theano graph of tc_gan/networks/ssn.py: EulerSSNCore.get_output_for
+// (:555-576) unrolled by Lasagne's CustomRecurrentLayer (:354-385), the outputs of
+// EulerSSNModel (:619-633: time_avg, dynamics_penalty, rate_penalty) and Theano's
+// autodiff through the scan.
+//
+//   forward   r_0 = 0,  r_{k+1} = (1-eps) r_k + eps f(W r_k + I),  k = 0..seqlen-1
+//             traj[t] = r_{t+1};  gain[t] = eps f'(W r_t + I)
+//   backward  lambda_k = d_k + (1-eps) lambda_{k+1} + W^T q_k,  q_k = gain[k] * lambda_{k+1}
+//             dL/dW = sum_k q_k r_k^T   (a [2N x K] x [K x 2N] contraction, K = seqlen * nb)
+//             dL/dtheta = <dL/dW, dW/dtheta>  fused into the contraction's epilogue
+//
+// Forward and the adjoint recursion run on the cluster-resident machinery of K1/K2
+// (W, then W^T, in distributed shared memory; one DSMEM exchange per time step).
+#include "ssn_cluster_core.cuh"
 #include "ssn_launch.h"
+
 namespace ssn {
-int launch_euler_forward(const ssn_solver &, int, int, int, const float *, const ssn_jds &, const float *, int, int,
-                         int, double, float *, double *, float *, float *, int *, cudaStream_t) {
-    set_error("euler forward: not built yet");
-    return -1;
+
+bool choose_cluster_shape(int n_sites, ClusterShape *out, int smem_limit, int *variant);
+
+struct EulerArgs {
+    int nz, nb, n_sites;
+    ClusterShape shape;
+    const float *z;
+    WeightConst wc;
+    const float *ext;
+    long long ext_stride_z;
+    int seqlen, skip;
+    float threshold;
+    int *work_counter;
+    IoConst<float> io;
+    double eps_E, eps_I;
+    // forward
+    float *time_avg;
+    double *penalties;
+    float *traj, *gain;
+    // backward
+    const float *g_avg;
+    double w_dyn, w_rate;
+    const float *traj_in, *gain_in;
+    float *adj;
+};
+
+template <int TI, int KL, int NWARPS, bool BACKWARD>
+__global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const EulerArgs a) {
+    using Own = Owner<TI, KL>;
+    constexpr int TO = Own::TO;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[2];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int csize = a.shape.csize;
+    const int dim = a.shape.dim, kpad = a.shape.kpad, rpc = a.shape.rpc, N = a.n_sites;
+    const int P = panel_P(kpad);
+    const SmemLayout L = smem_layout(a.shape, a.n_sites);
+    float *Wsm = reinterpret_cast<float *>(smem + L.w_off);
+    float *Xf = reinterpret_cast<float *>(smem + L.x_off);
+    const float4 *X4 = reinterpret_cast<const float4 *>(smem + L.x_off);
+    float *gtab = reinterpret_cast<float *>(smem + L.gtab_off);
+    Misc *misc = reinterpret_cast<Misc *>(smem + L.misc_off);
+
+    const int tid = threadIdx.x, nthreads = NWARPS * 32;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int kl = lane % KL;
+    const int grp = warp * (32 / KL) + lane / KL;
+    const int row_base = rank * rpc;
+    const int rows_here = max(0, min(rpc, dim - row_base));
+
+    int wrow[TI];
+#pragma unroll
+    for (int t = 0; t < TI; ++t) wrow[t] = min(grp * TI + t, rows_here - 1);
+    const int my_stim = Own::stim(kl);
+    const int own0 = grp * TI + Own::first_row(kl);
+    bool valid[TO];
+#pragma unroll
+    for (int u = 0; u < TO; ++u)
+        valid[u] = (Own::first_row(kl) + u < TI) && (own0 + u < rows_here);
+
+    unsigned xpeer[MAX_CLUSTER];
+#pragma unroll
+    for (int p = 0; p < MAX_CLUSTER; ++p) xpeer[p] = map_to_rank(smem_u32(Xf), p < csize ? p : 0);
+
+    build_profile_table(a.wc, N, gtab, tid, nthreads);
+    for (int i = tid; i < 2 * 2 * P * 4; i += nthreads) Xf[i] = 0.f;
+    if (tid < 2) red[tid] = 0.0;
+    __syncthreads();
+
+    const int n_chunks = (a.nb + TB - 1) / TB;
+    const unsigned buf_bytes = 2u * (unsigned)P * 16u;
+    const int seqlen = a.seqlen, skip = a.skip;
+    const int T = seqlen - skip;
+    double pen_dyn = 0.0, pen_rate = 0.0;
+
+    for (;;) {
+        if (rank == 0 && tid == 0) {
+            const int n = atomicAdd(a.work_counter, 1);
+            for (int p = 0; p < csize; ++p) st_cluster_u32(map_to_rank(smem_u32(&misc->next_net), p), (unsigned)n);
+        }
+        cluster.sync();
+        const int net = misc->next_net;
+        if (net >= a.nz) break;
+        const float *z_net = a.z + (size_t)net * dim * dim;
+
+        load_matrix_slice<BACKWARD>(Wsm, z_net, SSN_W_FROM_Z, a.wc, gtab, N, dim, kpad, row_base, rows_here,
+                                    tid, nthreads);
+
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int b0 = chunk * TB;
+            const int nact = min(TB, a.nb - b0);
+            const bool active = my_stim < nact;
+            const int stim_g = b0 + my_stim;
+
+            unsigned xoff[TO];
+            double eps_own[TO], state[TO];             // r_k (forward) or lambda_{k+1} (backward)
+            size_t goff[TO];                           // offset of (stim, row) inside one time slice
+#pragma unroll
+            for (int u = 0; u < TO; ++u) {
+                xoff[u] = 0u; eps_own[u] = 0.0; state[u] = 0.0; goff[u] = 0;
+                if (valid[u]) {
+                    const int gr = row_base + own0 + u;
+                    xoff[u] = 4u * (unsigned)panel_index(P, 0, gr, my_stim);
+                    eps_own[u] = gr < N ? a.eps_E : a.eps_I;
+                    goff[u] = (size_t)stim_g * dim + gr;
+#pragma unroll
+                    for (int p = 0; p < MAX_CLUSTER; ++p)
+                        if (p < csize) st_cluster_f32(xpeer[p] + xoff[u], 0.f);
+                }
+            }
+            const size_t slice = (size_t)a.nb * dim;                    // one time step of one network
+            const size_t net_base = (size_t)net * seqlen * slice;
+
+            if (!BACKWARD) {
+                float ext_own[TO];
+                double avg[TO];
+#pragma unroll
+                for (int u = 0; u < TO; ++u) {
+                    avg[u] = 0.0;
+                    ext_own[u] = (valid[u] && active)
+                        ? __ldg(a.ext + (size_t)net * a.ext_stride_z + goff[u]) : 0.f;
+                }
+                cluster.sync();
+                int buf = 0;
+                for (int t = 0; t < seqlen; ++t) {
+                    float acc[TI][TB], v[TO];
+                    contract_panel<TI, KL>(acc, Wsm, X4, P, kpad, buf, wrow, kl);
+                    reduce_scatter<TI, KL>(acc, v, kl);
+                    const int nbuf = buf ^ 1;
+#pragma unroll
+                    for (int u = 0; u < TO; ++u)
+                        if (valid[u]) {
+                            const float vt = v[u] + ext_own[u];
+                            const float fv = io_eval<float>(a.io, vt);
+                            const double r_old = state[u];
+                            const double r_new = r_old + ((double)fv - r_old) * eps_own[u];
+                            state[u] = r_new;
+                            if (active) {
+                                if (t >= skip) {
+                                    avg[u] += r_new;
+                                    pen_rate += fmax(r_new - (double)a.threshold, 0.0);
+                                    if (t > skip) pen_dyn += (r_new - r_old) * (r_new - r_old);
+                                }
+                                const size_t o = net_base + (size_t)t * slice + goff[u];
+                                if (a.traj) a.traj[o] = (float)r_new;
+                                if (a.gain) a.gain[o] = (float)eps_own[u] * io_gain<float>(a.io, vt);
+                            }
+                            const unsigned off = xoff[u] + (nbuf ? buf_bytes : 0u);
+                            const float rf = (float)r_new;
+#pragma unroll
+                            for (int p = 0; p < MAX_CLUSTER; ++p)
+                                if (p < csize) st_cluster_f32(xpeer[p] + off, rf);
+                        }
+                    cluster.sync();
+                    buf = nbuf;
+                }
+#pragma unroll
+                for (int u = 0; u < TO; ++u)
+                    if (valid[u] && active) a.time_avg[(size_t)net * slice + goff[u]] = (float)(avg[u] / T);
+            } else {
+                // ---- adjoint recursion, k = seqlen .. 1 (array index tp = k - 1) ----
+                float gavg[TO], r_cur[TO], r_next[TO];
+#pragma unroll
+                for (int u = 0; u < TO; ++u) {
+                    gavg[u] = 0.f; r_cur[u] = 0.f; r_next[u] = 0.f;
+                    if (valid[u] && active) {
+                        gavg[u] = __ldg(a.g_avg + (size_t)net * slice + goff[u]) / (float)T;
+                        r_cur[u] = __ldg(a.traj_in + net_base + (size_t)(seqlen - 1) * slice + goff[u]);
+                    }
+                }
+                cluster.sync();
+                int buf = 0;
+                for (int tp = seqlen - 1; tp >= 0; --tp) {
+                    const int k = tp + 1;
+                    float y[TO];
+#pragma unroll
+                    for (int u = 0; u < TO; ++u) y[u] = 0.f;
+                    if (k < seqlen) {                   // q_k was published at the end of the previous step
+                        float acc[TI][TB];
+                        contract_panel<TI, KL>(acc, Wsm, X4, P, kpad, buf, wrow, kl);
+                        reduce_scatter<TI, KL>(acc, y, kl);
+                    }
+                    const int nbuf = buf ^ 1;
+#pragma unroll
+                    for (int u = 0; u < TO; ++u)
+                        if (valid[u]) {
+                            float r_prev = 0.f;
+                            double lam = 0.0;
+                            if (active) {
+                                if (tp > 0) r_prev = __ldg(a.traj_in + net_base + (size_t)(tp - 1) * slice + goff[u]);
+                                double d = 0.0;
+                                if (k >= skip + 1) {
+                                    d = (double)gavg[u];
+                                    if (r_cur[u] > a.threshold) d += a.w_rate;
+                                    if (k >= skip + 2) d += 2.0 * a.w_dyn * ((double)r_cur[u] - (double)r_prev);
+                                    if (k <= seqlen - 1) d -= 2.0 * a.w_dyn * ((double)r_next[u] - (double)r_cur[u]);
+                                }
+                                lam = d + (1.0 - eps_own[u]) * state[u] + (double)y[u];
+                            }
+                            state[u] = lam;                           // lambda_k
+                            // q_{k-1} = gain[k-1] * lambda_k, paired with r_{k-1} = traj[tp-1]
+                            float q = 0.f;
+                            if (active && tp > 0) {
+                                q = __ldg(a.gain_in + net_base + (size_t)tp * slice + goff[u]) * (float)lam;
+                                a.adj[net_base + (size_t)(tp - 1) * slice + goff[u]] = q;
+                            }
+                            if (active && tp == seqlen - 1)
+                                a.adj[net_base + (size_t)tp * slice + goff[u]] = 0.f;   // q_seqlen = 0
+                            r_next[u] = r_cur[u];
+                            r_cur[u] = r_prev;
+                            const unsigned off = xoff[u] + (nbuf ? buf_bytes : 0u);
+#pragma unroll
+                            for (int p = 0; p < MAX_CLUSTER; ++p)
+                                if (p < csize) st_cluster_f32(xpeer[p] + off, q);
+                        }
+                    cluster.sync();
+                    buf = nbuf;
+                }
+            }
+            cluster.sync();
+        }
+    }
+    if (!BACKWARD) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pen_dyn += __shfl_xor_sync(0xffffffffu, pen_dyn, o);
+            pen_rate += __shfl_xor_sync(0xffffffffu, pen_rate, o);
+        }
+        if (lane == 0) { atomicAdd(&red[0], pen_dyn); atomicAdd(&red[1], pen_rate); }
+        __syncthreads();
+        if (tid < 2) atomicAdd(a.penalties + tid, red[tid]);
+    }
 }
-int launch_euler_backward(const ssn_solver &, int, int, int, const float *, const ssn_jds &, int, int, double,
-                          const float *, double, double, const float *, const float *, float *, double *, int *,
-                          cudaStream_t) {
-    set_error("euler backward: not built yet");
-    return -1;
+
+// ------------------------------------------------------------------------------------
+// dL/dtheta = < sum_k q_k r_k^T , dW/dtheta >:  per network a [dim x K] x [K x dim]
+// contraction (K = seqlen * nb) tiled 64 x 64 per CTA, FP32 FFMA, with the product
+// against dW/dtheta (z re-read, Gaussian profile recomputed) fused into the epilogue.
+// ------------------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) ssn_bptt_param_grad_kernel(int n_sites, long long K, const float *adj,
+                                                                  const float *traj, const float *z,
+                                                                  WeightConst wc, double *grad) {
+    __shared__ float As[GK][GT + 4], Bs[GK][GT + 4];
+    __shared__ double red[12];
+    const int dim = 2 * n_sites;
+    const int tiles = (dim + GT - 1) / GT;
+    const int net = blockIdx.x / (tiles * tiles);
+    const int ti = (blockIdx.x / tiles) % tiles, tj = blockIdx.x % tiles;
+    const int i0 = ti * GT, j0 = tj * GT;
+    const float *A = adj + (size_t)net * K * dim, *B = traj + (size_t)net * K * dim;
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;                 // 16 x 16 threads, 4 x 4 outputs each
+    if (tid < 12) red[tid] = 0.0;
+    float c[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[p][q] = 0.f;
+    const int lk = tid / 64, lc = tid % 64;                 // loader: 4 k-rows x 64 columns per pass
+    for (long long k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+        for (int p = 0; p < GK / 4; ++p) {
+            const long long k = k0 + lk + 4 * p;
+            As[lk + 4 * p][lc] = (k < K && i0 + lc < dim) ? __ldg(A + k * dim + i0 + lc) : 0.f;
+            Bs[lk + 4 * p][lc] = (k < K && j0 + lc < dim) ? __ldg(B + k * dim + j0 + lc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            const float4 av = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) c[p][q] = fmaf(aa[p], bb[q], c[p][q]);
+        }
+        __syncthreads();
+    }
+    const float *z_net = z + (size_t)net * dim * dim;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + ty * 4 + p, j = j0 + tx * 4 + q;
+            if (i < dim && j < dim) {
+                const int ah = i >= n_sites, bh = j >= n_sites, ab = ah * 2 + bh;
+                const float zz = __ldg(z_net + (size_t)i * dim + j);
+                const float x = (float)((i - ah * n_sites) - (j - bh * n_sites)) * wc.dx;
+                const float gq = expf(-x * x * wc.inv2s2[ab]);
+                const float gG = gq * c[p][q];
+                const float sgn = bh == 0 ? 1.f : -1.f;
+                atomicAdd(&red[ab], (double)(sgn * gG));
+                atomicAdd(&red[4 + ab], (double)(sgn * gG * zz));
+                atomicAdd(&red[8 + ab], (double)(gG * x * x * wc.invS3[ab] * fmaf(wc.sD[ab], zz, wc.sJ[ab])));
+            }
+        }
+    __syncthreads();
+    if (tid < 12 && red[tid] != 0.0) atomicAdd(grad + tid, red[tid]);
 }
+
+// ------------------------------------------------------------------------------------
+
+typedef void (*EulerKernel)(const EulerArgs);
+struct EulerVariant { EulerKernel fwd, bwd; int threads; };
+static const EulerVariant kEulerVariants[] = {
+    {ssn_euler_cluster_kernel<4, 16, 8, false>, ssn_euler_cluster_kernel<4, 16, 8, true>, 256},
+    {ssn_euler_cluster_kernel<7, 16, 8, false>, ssn_euler_cluster_kernel<7, 16, 8, true>, 256},
+    {ssn_euler_cluster_kernel<7, 8, 8, false>, ssn_euler_cluster_kernel<7, 8, 8, true>, 256},
+};
+
+static int launch_euler(bool backward, EulerArgs &a, int n_sites, int nz, int *counter, cudaStream_t stream) {
+    int dev = 0, limit = 0, variant = 0;
+    SSN_CUDA(cudaGetDevice(&dev));
+    SSN_CUDA(cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (!choose_cluster_shape(n_sites, &a.shape, limit - 256, &variant)) {
+        set_error("euler kernel: 2N=%d does not fit a cluster of %d CTAs", 2 * n_sites, MAX_CLUSTER);
+        return -1;
+    }
+    EulerKernel fn = backward ? kEulerVariants[variant].bwd : kEulerVariants[variant].fwd;
+    const int smem = smem_layout(a.shape, n_sites).total;
+    SSN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    a.work_counter = counter;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.shape.csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(a.shape.csize, 1, 1);
+    cfg.blockDim = dim3(kEulerVariants[variant].threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    SSN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
+    if (max_clusters < 1) { set_error("euler kernel: no resident cluster"); return -1; }
+    cfg.gridDim = dim3(std::min(max_clusters, nz) * a.shape.csize, 1, 1);
+    SSN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    SSN_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    count_launch();
+    return 0;
 }
+
+static void fill_common(EulerArgs &a, const ssn_solver &sv, int nz, int nb, int n_sites, const float *z,
+                        const ssn_jds &jds, int seqlen, int skip, double threshold) {
+    a.nz = nz; a.nb = nb; a.n_sites = n_sites;
+    a.z = z; a.wc = make_weight_const(jds, n_sites);
+    a.seqlen = seqlen; a.skip = skip; a.threshold = (float)threshold;
+    a.io = make_io_const<float>(sv.io_type, sv.k, sv.n, sv.rate_soft_bound, sv.rate_hard_bound);
+    a.eps_E = sv.dt / sv.tau_E; a.eps_I = sv.dt / sv.tau_I;
+}
+
+int launch_euler_forward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
+                         const float *ext, int ext_per_network, int seqlen, int skip_steps, double threshold,
+                         float *time_avg, double *penalties, float *traj, float *gain, int *counter,
+                         cudaStream_t stream) {
+    SSN_CUDA(cudaMemsetAsync(penalties, 0, 2 * sizeof(double), stream));
+    if (nz <= 0 || nb <= 0) return 0;
+    EulerArgs a = {};
+    fill_common(a, sv, nz, nb, n_sites, z, jds, seqlen, skip_steps, threshold);
+    a.ext = ext; a.ext_stride_z = ext_per_network ? (long long)nb * 2 * n_sites : 0;
+    a.time_avg = time_avg; a.penalties = penalties; a.traj = traj; a.gain = gain;
+    return launch_euler(false, a, n_sites, nz, counter, stream);
+}
+
+int launch_euler_backward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
+                          int seqlen, int skip_steps, double threshold, const float *grad_time_avg,
+                          double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
+                          double *grad, int *counter, cudaStream_t stream) {
+    SSN_CUDA(cudaMemsetAsync(grad, 0, 12 * sizeof(double), stream));
+    if (nz <= 0 || nb <= 0) return 0;
+    EulerArgs a = {};
+    fill_common(a, sv, nz, nb, n_sites, z, jds, seqlen, skip_steps, threshold);
+    a.g_avg = grad_time_avg; a.w_dyn = w_dyn; a.w_rate = w_rate;
+    a.traj_in = traj; a.gain_in = gain; a.adj = adj;
+    int rc = launch_euler(true, a, n_sites, nz, counter, stream);
+    if (rc) return rc;
+    const int dim = 2 * n_sites, tiles = (dim + GT - 1) / GT;
+    ssn_bptt_param_grad_kernel<<<nz * tiles * tiles, 256, 0, stream>>>(
+        n_sites, (long long)seqlen * nb, adj, traj, z, a.wc, grad);
+    SSN_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace ssn

@@ -76,3 +76,60 @@ def test_fixed_point_autograd_function(ops, oracle):
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
     with pytest.raises(Exception):
         ops.fixed_points(tens(z).cpu(), J, D, S, tens(exts).cpu())
+
+
+def euler_oracle(oracle, z, jds, exts, seqlen, skip, eps, io_type, thr, G, c_dyn, c_rate):
+    import torch
+    t64 = lambda a, g=False: torch.tensor(np.asarray(a), dtype=torch.float64, requires_grad=g)
+    J, D, S = (t64(jds[k], True) for k in 'JDS')
+    avg, dyn, rate = oracle.euler_unroll_torch(t64(z), J, D, S, t64(exts), seqlen, skip, eps[0], eps[1],
+                                               io_type=io_type, rate_penalty_threshold=thr)
+    loss = (avg * t64(G)).sum() + c_dyn * dyn + c_rate * rate
+    loss.backward()
+    return avg.detach().numpy(), float(dyn.detach()), float(rate.detach()), J.grad.numpy(), D.grad.numpy(), S.grad.numpy()
+
+
+@pytest.mark.parametrize('n_sites,nz,nb,seqlen,skip,io_type', [
+    (10, 2, 8, 60, 40, 'asym_tanh'), (25, 3, 5, 40, 25, 'asym_tanh'), (51, 2, 8, 30, 20, 'asym_power'),
+    (30, 2, 11, 24, 0, 'asym_linear'), (201, 1, 8, 12, 6, 'asym_tanh')])
+def test_euler_unroll_forward_backward(ops, oracle, n_sites, nz, nb, seqlen, skip, io_type):
+    """K3/K4 against torch float64 autograd through the restated Euler unroll
+    (tc_gan/networks/ssn.py:555-576, 619-633): outputs to rtol 1e-4, gradients to 1e-3.
+    A low rate threshold makes the rate penalty and its gradient non-trivial."""
+    import torch
+    jds = oracle.new_JDS()
+    bw = oracle.DEFAULT_BANDWIDTHS if nb == 8 else np.linspace(0.05, 1, nb)
+    exts = oracle.stimulus_input(bw, n_sites)
+    rs = np.random.RandomState(seqlen + n_sites)
+    z = rs.rand(nz, 2 * n_sites, 2 * n_sites).astype(np.float32).astype(np.float64)
+    G = rs.randn(nz, nb, 2 * n_sites)
+    eps, thr, c_dyn, c_rate = (0.01, 0.1), 0.5, 3.0, 2.0
+    avg_o, dyn_o, rate_o, dJ, dD, dS = euler_oracle(oracle, z, jds, exts, seqlen, skip, eps, io_type, thr,
+                                                    G, c_dyn, c_rate)
+    J, D, S = (tens(jds[k], torch.float64, grad=True) for k in 'JDS')
+    avg, dyn, rate = ops.euler_ssn(tens(z), J, D, S, tens(exts), seqlen=seqlen, skip_steps=skip, dt=0.1,
+                                   tau_E=10.0, tau_I=1.0, io_type=io_type, rate_penalty_threshold=thr)
+    np.testing.assert_allclose(avg.detach().cpu().numpy(), avg_o, rtol=1e-4, atol=1e-5)
+    if seqlen - skip > 1:
+        np.testing.assert_allclose(float(dyn), dyn_o, rtol=1e-4)
+    np.testing.assert_allclose(float(rate), rate_o, rtol=1e-4)
+    loss = (avg * tens(G)).sum() + c_dyn * dyn + c_rate * rate
+    loss.backward()
+    for got, want in ((J.grad, dJ), (D.grad, dD), (S.grad, dS)):
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+
+
+def test_euler_long_unroll_reaches_fixed_point(ops, oracle):
+    """tc_gan/networks/tests/test_euler_ssn.py:29-72 with our two CUDA paths: the last
+    state of a long Euler unroll equals the fixed-point solver's answer (rtol=atol=5e-4)."""
+    import torch
+    n_sites, nz = 10, 2
+    jds = oracle.new_JDS()
+    exts = oracle.stimulus_input(oracle.DEFAULT_BANDWIDTHS, n_sites)
+    z = np.random.RandomState(n_sites * nz).rand(nz, 2 * n_sites, 2 * n_sites)
+    J, D, S = (tens(jds[k], torch.float64) for k in 'JDS')
+    avg, _, _ = ops.euler_ssn(tens(z), J, D, S, tens(exts), seqlen=4000, skip_steps=3999)
+    solver = ops.make_solver(atol=1e-10, max_iter=100000)       # as the reference test; float64 kernel
+    R, status, _ = ops.fixed_points(tens(z), J, D, S, tens(exts), solver=solver, precise=True)
+    assert (status == 0).all()
+    np.testing.assert_allclose(avg.cpu().numpy(), R.cpu().numpy(), rtol=5e-4, atol=5e-4)
