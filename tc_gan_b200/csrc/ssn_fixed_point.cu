@@ -13,8 +13,10 @@
 // W streamed from L2) used by the reference-ABI single-solve symbols and by
 // `precise` batched calls.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include "ssn_cluster_core.cuh"
+#include "ssn_launch.h"
 
 namespace ssn {
 
@@ -422,6 +424,11 @@ static int plan_fixed_point(int n_sites, int nz, FpLaunchPlan *plan) {
 }
 
 int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters) {
+    if (!getenv("SSN_FORCE_SMEM_KERNEL")) {
+        ssn_solver sv = {};
+        sv.io_type = SSN_IO_TANH; sv.k = 0.01; sv.n = 2.2; sv.rate_soft_bound = 200; sv.rate_hard_bound = 1000;
+        if (regw_occupancy(sv, n_sites, cluster_size, resident_clusters) == 0) return 0;
+    }
     FpLaunchPlan plan;
     int rc = plan_fixed_point(n_sites, 0, &plan);
     if (rc) return rc;
@@ -435,8 +442,19 @@ int launch_fixed_point_f32(const ssn_solver &sv, int nz, int nb, int n_sites, in
                            const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
                            float *R, int *status, int *iters, int *counter, cudaStream_t stream) {
     if (nz <= 0 || nb <= 0) return 0;
+    const int n_solves_all = nz * nb;
+    int rc = getenv("SSN_FORCE_SMEM_KERNEL") ? 1 : launch_fixed_point_regw(sv, nz, nb, n_sites, w_kind, w, jds, ext,
+                                                                          ext_per_network, r_init, R, status, iters,
+                                                                          counter, stream);
+    if (rc == 0) {
+        ssn_status_fixup_kernel<<<(n_solves_all * 32 + 255) / 256, 256, 0, stream>>>(R, status, n_solves_all, 2 * n_sites);
+        SSN_CUDA(cudaGetLastError());
+        count_launch();
+        return 0;
+    }
+    if (rc != 1) return rc;
     FpLaunchPlan plan;
-    int rc = plan_fixed_point(n_sites, nz, &plan);
+    rc = plan_fixed_point(n_sites, nz, &plan);
     if (rc) return rc;
     FpArgs a = {};
     a.nz = nz; a.nb = nb; a.n_sites = n_sites;

@@ -11,6 +11,11 @@ int launch_fixed_point_f64(const ssn_solver &sv, int nz, int nb, int n_sites, co
                            const double *ext, int ext_per_network, const double *r_init,
                            double *R, int *status, int *iters, bool nonfinite_fixup, cudaStream_t stream);
 int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters);
+// register-resident-W kernel; returns 1 when the shape is outside its range
+int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
+                            const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
+                            float *R, int *status, int *iters, int *counter, cudaStream_t stream);
+int regw_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *resident_clusters);
 
 int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                         const float *ext, int ext_per_network, const float *R, const float *g, double rtol,

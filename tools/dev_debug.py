@@ -13,4 +13,3 @@ R, err, its = ssnode.fixed_points_batch(W, exts, k=0.01, n=2.2)
 print('status', err.tolist(), 'iters', its.tolist(), 'ref iters', it.tolist())
 d = np.abs(R - Ro)
 print('err by stim', d.max(axis=(0, 2)))
-print('err by row (net0, stim 3):', np.round(d[0, 3], 4).tolist())
