@@ -22,12 +22,19 @@
 // |r_new - r_old| < atol first holds then matches the float64 reference solver
 // (tc_gan/ext/ssnode.c:84-96) instead of jittering by tens of sweeps.
 #include <algorithm>
+#include <cstdlib>
 #include "ssn_cluster_core.cuh"
 #include "ssn_launch.h"
 
 namespace ssn {
 
 constexpr int RW_TI = 7, RW_WARPS = 8, RW_THREADS = 256, RW_ROWS = RW_TI * RW_WARPS;
+// State panel: one block per (source CTA, warp): 7 float4 rows of stimuli 0..3, 7 float4 rows of
+// stimuli 4..7, one 16-byte slot whose first word carries the warp's flags.  A warp publishes its
+// block to a peer CTA with ONE cp.async.bulk (one mbarrier transaction per block, not per element).
+constexpr int RW_BLK_SLOTS = 2 * RW_TI + 1, RW_BLK_BYTES = RW_BLK_SLOTS * 16;          // 15 slots, 240 B
+constexpr int RW_ZERO_SLOT = MAX_CLUSTER * RW_WARPS * RW_BLK_SLOTS;                     // slot 960: always 0
+constexpr int RW_BUF_BYTES = (RW_ZERO_SLOT + 1) * 16;
 constexpr int TAB_PER_UNIT = 16;                       // table nodes per unit of v
 constexpr double TAB_V_MIN = 1.0;
 
@@ -46,23 +53,29 @@ struct RwArgs {
     IoConst<float> iof;
     double eps_E, eps_I, atol, r_hard, t_first;        // t_first: first refresh threshold on |dr|
     int max_iter, check_hard, tab_nodes;
+    int dbg;                                           // development switches (SSN_DBG), 0 in production
 };
 
 struct RwSmem {
-    int x_off, xe_off, tab_off, gtab_off, misc_off, total;
+    int x_off, xe_off, tab_off, gtab_off, state_off, misc_off, total;
 };
+// per-thread float64 state of the owner lanes, kept in shared memory so that the sweep loop's
+// registers hold only the W tile and the accumulators: r, r_ref, v_ref as [4][256] doubles, ext as [4][256] floats
+constexpr int RW_STATE_BYTES = 3 * 4 * RW_THREADS * 8 + 4 * RW_THREADS * 4;
 struct RwMisc {
     unsigned long long full[2], xfull;
-    unsigned flagw[2][MAX_CLUSTER][RW_WARPS];
+    double tlevel[8];                        // refresh ladder: thresholds on max|dr| by level, 0 = exhausted
+    unsigned pdelta[MAX_CLUSTER];
     int next_net;
 };
 __host__ __device__ inline RwSmem rw_smem_layout(int kpad, int n_sites, int tab_nodes) {
     RwSmem L;
     int o = 0;
-    L.x_off = o;    o += 2 * 2 * kpad * 16;            // [buf][plane][column] float4
+    L.x_off = o;    o += 2 * RW_BUF_BYTES;             // [buf][source CTA][warp] blocks of RW_BLK_BYTES + a zero slot
     L.xe_off = o;   o += 2 * TB * kpad * 4;            // exact-pass columns: hi[8][kpad], lo[8][kpad]
     L.tab_off = o;  o += tab_nodes * 32;               // cubic table of f: 4 doubles per node
     L.gtab_off = o; o += ((4 * n_sites * 4 + 15) / 16) * 16;
+    L.state_off = o; o += RW_STATE_BYTES;
     L.misc_off = o; o += 1024;
     L.total = o;
     return L;
@@ -79,9 +92,28 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned done = 0;
     while (!done)
         asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;"
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;"
             " selp.u32 %0, 1, 0, p; }"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(unsigned addr, float4 v, unsigned bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                   "r"(__float_as_uint(v.w)), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_async_v2(unsigned addr, float a, float b, unsigned bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+                 ::"r"(addr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_release(unsigned bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_to_peer(unsigned dst_remote, unsigned src_local, unsigned bytes, unsigned bar_remote) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_remote), "r"(src_local), "r"(bytes), "r"(bar_remote) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void st_async_u32(unsigned addr, unsigned v, unsigned bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
@@ -92,7 +124,7 @@ __device__ __forceinline__ void st_async_u32(unsigned addr, unsigned v, unsigned
 // accurate float for v < 1 (|f| < k: absolute error ~1e-9 k), closed form above the table.
 __device__ __forceinline__ double io_eval_table(const RwArgs &a, const double *tab, double v) {
     if (!(v > 0.0)) return v != v ? v : 0.0;
-    if (v < TAB_V_MIN) return (double)(a.iof.k * powf((float)v, a.iof.n));
+    if (v < TAB_V_MIN) return (double)(a.iof.k * exp2f(a.iof.n * __log2f((float)v)));   // |f| < k, abs. error ~1e-8 k
     const double x = (v - TAB_V_MIN) * TAB_PER_UNIT;
     const bool upper = a.io.io_type != SSN_IO_POWER && v > a.io.v0;
     if (!upper && x < (double)(a.tab_nodes - 1)) {
@@ -116,46 +148,49 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
     const int csize = a.csize, dim = a.dim, kpad = a.kpad, rpc = a.rpc, N = a.n_sites;
     const RwSmem L = rw_smem_layout(kpad, N, a.tab_nodes);
     float *Xf = reinterpret_cast<float *>(smem + L.x_off);
-    const float4 *X4 = reinterpret_cast<const float4 *>(smem + L.x_off);
     float *xe = reinterpret_cast<float *>(smem + L.xe_off);
     double *tab = reinterpret_cast<double *>(smem + L.tab_off);
     float *gtab = reinterpret_cast<float *>(smem + L.gtab_off);
     RwMisc *misc = reinterpret_cast<RwMisc *>(smem + L.misc_off);
+    double *sR = reinterpret_cast<double *>(smem + L.state_off) + threadIdx.x;        // [i][256]
+    double *sRref = sR + 4 * RW_THREADS, *sVref = sR + 8 * RW_THREADS;
+    float *sExt = reinterpret_cast<float *>(smem + L.state_off + 3 * 4 * RW_THREADS * 8) + threadIdx.x;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = rank * rpc;
     const int rows_here = max(0, min(rpc, dim - row_base));
     const int row0 = warp * RW_TI;                                  // first local row of this warp
 
-    // ownership after the 32-lane reduce-scatter: stimulus (lane >> 2), two rows of the warp's seven
-    const int my_stim = lane >> 2;
-    const int t0 = ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
-    bool valid[2];
-    int grow[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        valid[u] = (t0 + u < RW_TI) && (row0 + t0 + u < rows_here);
-        grow[u] = row_base + row0 + t0 + u;
-    }
+    // ownership after the 32-lane reduce-scatter: lane bit 4 -> stimulus half h (stimuli 4h..4h+3),
+    // bits 3..1 -> row t of the warp's seven; the even lane of each pair is the owner.
+    const int my_half = lane >> 4;
+    const int my_t = (lane >> 1) & 7;
+    const bool owner = ((lane & 1) == 0) && my_t < RW_TI && (row0 + my_t < rows_here);
+    const int grow = row_base + row0 + my_t;                        // global row of the owned outputs
+    const int sid = lane & 7;                                       // stimulus whose status this lane tracks
 
     const unsigned x_local = smem_u32(Xf), xe_local = smem_u32(xe);
     const unsigned full_local[2] = {smem_u32(&misc->full[0]), smem_u32(&misc->full[1])};
     const unsigned xfull_local = smem_u32(&misc->xfull);
-    const unsigned flag_local = smem_u32(&misc->flagw[0][0][0]);
-    // shared::cluster address of the same offset in CTA p = local address + pdelta_of(p)
+    // shared::cluster address of the same offset in CTA p = local address + pdelta[p]
     // (the cluster window of every CTA is laid out identically, so one subtraction gives the offset)
-    auto pdelta_of = [&](int p) -> unsigned { return map_to_rank(x_local, (unsigned)p) - x_local; };
+    if (tid < MAX_CLUSTER) misc->pdelta[tid] = map_to_rank(x_local, (unsigned)(tid < csize ? tid : 0)) - x_local;
+    const volatile unsigned *pdelta = misc->pdelta;
 
     // ---- one-time setup ----
+    if (tid < 8) {
+        double t = a.t_first;
+        for (int l = 0; l < tid; ++l) t *= (1.0 / 64.0);
+        misc->tlevel[tid] = (tid == 7 || t <= a.atol) ? 0.0 : t;
+    }
     if (tid == 0) {
-        mbar_init(full_local[0], 1);
-        mbar_init(full_local[1], 1);
+        mbar_init(full_local[0], 1 + RW_WARPS);          // the arming thread + one release-arrive per local warp
+        mbar_init(full_local[1], 1 + RW_WARPS);
         mbar_init(xfull_local, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 2 * 2 * kpad * 4; i += RW_THREADS) Xf[i] = 0.f;
+    for (int i = tid; i < 2 * RW_BUF_BYTES / 4; i += RW_THREADS) Xf[i] = 0.f;
     for (int i = tid; i < 2 * TB * kpad; i += RW_THREADS) xe[i] = 0.f;
-    for (int i = tid; i < 2 * MAX_CLUSTER * RW_WARPS; i += RW_THREADS) (&misc->flagw[0][0][0])[i] = 0u;   // absent CTAs report nothing
     if (a.w_kind == SSN_W_FROM_Z) build_profile_table(a.wc, N, gtab, tid, RW_THREADS);
     for (int i = tid; i < a.tab_nodes; i += RW_THREADS) {           // cubic table of k v^n
         const double v = TAB_V_MIN + (double)i / TAB_PER_UNIT, h = 1.0 / TAB_PER_UNIT;
@@ -168,9 +203,21 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
     cluster.sync();
 
     unsigned ph[2] = {0u, 0u}, xph = 0u;
-    const unsigned tx_bytes = (unsigned)(dim * TB + csize * RW_WARPS) * 4u;
+    const unsigned tx_bytes = (a.dbg & 1) ? 0u : (unsigned)((csize - 1) * RW_WARPS * RW_BLK_BYTES);      // blocks arriving from peers
+    // slot (16-byte unit inside a buffer) of panel column j = c*32 + lane, two per register
+    unsigned colslot[(NC + 1) / 2];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const int j = c * 32 + lane;
+        unsigned slot = RW_ZERO_SLOT;
+        if (j < dim) {
+            const int cta = j / rpc, lr = j - cta * rpc, w = lr / RW_TI, t = lr - w * RW_TI;
+            slot = (unsigned)((cta * RW_WARPS + w) * RW_BLK_SLOTS + t);
+        }
+        if (c & 1) colslot[c / 2] |= slot << 16; else colslot[c / 2] = slot;
+    }
+    const unsigned my_block = (unsigned)((rank * RW_WARPS + warp) * RW_BLK_BYTES);      // byte offset in a buffer
     const int n_chunks = (a.nb + TB - 1) / TB;
-    const unsigned buf_bytes = 2u * (unsigned)kpad * 16u;
 
     for (;;) {
         // ---- next network from the global queue ----
@@ -206,49 +253,44 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
             const int b0 = chunk * TB;
             const int nact = min(TB, a.nb - b0);
-            const bool active = my_stim < nact;
-            const size_t sol = (size_t)net * a.nb + b0 + my_stim;
             const float *ext_net = a.ext + (size_t)net * a.ext_stride_z;
 
-            double r[2], r_ref[2], v_ref[2];
-            float eps_own[2], ext_own[2];
-            unsigned xoff[2];
+            // float64 state of the four (row, stimulus) outputs an owner lane holds lives in shared memory
+            const double eps_own = grow < N ? a.eps_E : a.eps_I;
+            unsigned levels = 0u;                            // refresh-ladder level of my four stimuli, 4 bits each
+            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                r[u] = 0.0; r_ref[u] = 0.0; v_ref[u] = 0.0; eps_own[u] = 0.f; ext_own[u] = 0.f; xoff[u] = 0u;
-                if (valid[u]) {
-                    eps_own[u] = grow[u] < N ? 0.f : 1.f;               // selector: E or I time constant
-                    xoff[u] = 4u * (unsigned)(((my_stim >> 2) * kpad + grow[u]) * 4 + (my_stim & 3));
-                    if (active) {
-                        ext_own[u] = __ldg(ext_net + (size_t)(b0 + my_stim) * dim + grow[u]);
-                        v_ref[u] = (double)ext_own[u];
-                        if (a.r_init) r[u] = (double)__ldg(a.r_init + sol * dim + grow[u]);
-                    }
+            for (int i = 0; i < 4; ++i) {
+                double r0 = 0.0;
+                float e = 0.f;
+                const int st = 4 * my_half + i;
+                if (owner && st < nact) {
+                    e = __ldg(ext_net + (size_t)(b0 + st) * dim + grow);
+                    if (a.r_init) r0 = (double)__ldg(a.r_init + ((size_t)net * a.nb + b0 + st) * dim + grow);
                 }
+                sR[i * RW_THREADS] = r0; sRref[i * RW_THREADS] = 0.0; sVref[i * RW_THREADS] = (double)e;
+                sExt[i * RW_THREADS] = e;
+                (&x0.x)[i] = (float)r0;
             }
-            // refresh ladder on max|dr| (uniform per stimulus); with r_init the first sweep refreshes
-            double t_next = a.t_first;
+            const unsigned xoff = my_block + 16u * (unsigned)(my_t + RW_TI * my_half);   // my float4 inside a buffer
             unsigned done = nact >= TB ? 0u : (0xffu << nact) & 0xffu;
-            unsigned force_refresh = a.r_init ? (~done & 0xffu) : 0u;
-            int my_status = 1, my_iters = a.max_iter;
+            unsigned force_refresh = a.r_init ? (~done & 0xffu) : 0u;   // with r_init the first sweep refreshes
+            int my_status = 1, my_iters = a.max_iter;                   // of stimulus `sid`
 
-            // ---- publish the initial panel (r - r_ref = 0 unless r_init: then r itself, refreshed at once) ----
+            // ---- publish the initial panel: r - r_ref (= r_init, refreshed at once, or 0) ----
             int buf = 0;
             if (tid == 0) mbar_arrive_expect_tx(full_local[0], tx_bytes);
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-                if (valid[u]) {
-                    const unsigned bits = __float_as_uint((float)(r[u] - r_ref[u]));
-#pragma unroll
-                    for (int p = 0; p < MAX_CLUSTER; ++p)
-                        if (p < csize) st_async_u32(x_local + xoff[u] + pdelta_of(p), bits, full_local[0] + pdelta_of(p));
-                }
+            if (owner) *reinterpret_cast<float4 *>(smem + L.x_off + xoff) = x0;
             if (lane == 0)
-#pragma unroll
-                for (int p = 0; p < MAX_CLUSTER; ++p)
-                    if (p < csize)
-                        st_async_u32(flag_local + 4u * (unsigned)((0 * MAX_CLUSTER + rank) * RW_WARPS + warp) + pdelta_of(p),
-                                     0x00ff0000u, full_local[0] + pdelta_of(p));     // "big" everywhere: no refresh yet
+                *reinterpret_cast<unsigned *>(smem + L.x_off + my_block + 2 * RW_TI * 16) = 0x00ff0000u;  // "big": no refresh yet
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_release(full_local[0]);
+            else if (lane <= csize - 1 && !(a.dbg & 1)) {
+                const int p = lane - 1 + (lane - 1 >= rank ? 1 : 0);            // the csize-1 peers
+                bulk_copy_to_peer(x_local + my_block + pdelta[p], x_local + my_block, RW_BLK_BYTES,
+                                  full_local[0] + pdelta[p]);
+            }
 
             for (int it = 1;; ++it) {
                 // ---- wait for the panel of this sweep and the flags of the previous one ----
@@ -256,43 +298,47 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                 ph[buf] ^= 1u;
                 unsigned F;
                 {
-                    const unsigned *fw = &misc->flagw[buf][0][0];
-                    unsigned f = fw[lane] | fw[lane + 32];                       // 8 CTAs x 8 warps = 64 words
-                    F = __reduce_or_sync(0xffffffffu, f);
+                    const unsigned char *xb = smem + L.x_off + buf * RW_BUF_BYTES + 2 * RW_TI * 16;
+                    F = __reduce_or_sync(0xffffffffu,
+                                         *reinterpret_cast<const unsigned *>(xb + lane * RW_BLK_BYTES) |
+                                         *reinterpret_cast<const unsigned *>(xb + (lane + 32) * RW_BLK_BYTES));
                 }
                 if (it > 1) {
                     const unsigned moving_all = F & 0xffu, above_all = (F >> 8) & 0xffu;
                     const unsigned conv_now = ~moving_all & ~done & 0xffu;       // ssnode.c:84-96 first ...
                     const unsigned hard_now = a.check_hard ? (above_all & ~done & ~conv_now & 0xffu) : 0u;  // ... then :98-102
-                    if ((conv_now >> my_stim) & 1u) { my_status = 0; my_iters = it - 1; }
-                    if ((hard_now >> my_stim) & 1u) { my_status = 2; my_iters = it - 1; }
+                    if ((conv_now >> sid) & 1u) { my_status = 0; my_iters = it - 1; }
+                    if ((hard_now >> sid) & 1u) { my_status = 2; my_iters = it - 1; }
                     done |= conv_now | hard_now;
                 }
                 if (done == 0xffu || it > a.max_iter) break;
 
                 // ---- reference-point refresh for stimuli whose max|dr| fell below their ladder threshold ----
-                const unsigned natural = ~(F >> 16) & ~done & 0xffu;     // max|dr| fell below the ladder threshold
+                const unsigned natural = ~(F >> 16) & ~done & 0xffu;
                 const unsigned req = natural | (force_refresh & ~done);
                 force_refresh = 0u;
                 if (req) {
                     const unsigned nreq = __popc(req);
                     if (tid == 0) mbar_arrive_expect_tx(xfull_local, nreq * (unsigned)dim * 8u);
-                    if ((req >> my_stim) & 1u) {
+                    if (owner) {
 #pragma unroll
-                        for (int u = 0; u < 2; ++u)
-                            if (valid[u]) {
-                                const float hi = (float)r[u];
-                                const float lo = (float)(r[u] - (double)hi);
-                                const unsigned o = 4u * (unsigned)(my_stim * kpad + grow[u]);
+                        for (int i = 0; i < 4; ++i) {
+                            const int st = 4 * my_half + i;
+                            if ((req >> st) & 1u) {
+                                const double ri = sR[i * RW_THREADS];
+                                const float hi = (float)ri;
+                                const float lo = (float)(ri - (double)hi);
+                                const unsigned o = 4u * (unsigned)(st * kpad + grow);
 #pragma unroll
                                 for (int p = 0; p < MAX_CLUSTER; ++p)
                                     if (p < csize) {
-                                        const unsigned bar = xfull_local + pdelta_of(p);
-                                        st_async_u32(xe_local + o + pdelta_of(p), __float_as_uint(hi), bar);
-                                        st_async_u32(xe_local + o + 4u * (unsigned)(TB * kpad) + pdelta_of(p),
+                                        const unsigned bar = xfull_local + pdelta[p];
+                                        st_async_u32(xe_local + o + pdelta[p], __float_as_uint(hi), bar);
+                                        st_async_u32(xe_local + o + 4u * (unsigned)(TB * kpad) + pdelta[p],
                                                      __float_as_uint(lo), bar);
                                     }
                             }
+                        }
                     }
                     mbar_wait(xfull_local, xph);
                     xph ^= 1u;
@@ -313,30 +359,26 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                                 accf[t] = fmaf(wreg[t][c], l, accf[t]);
                             }
                         }
+                        double mine = 0.0;
 #pragma unroll
                         for (int t = 0; t < RW_TI; ++t) {
                             double v = accd[t] + (double)accf[t];
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                            accd[t] = v;
+                            mine = (t == my_t) ? v : mine;
                         }
-                        if (my_stim == s) {
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                double v = 0.0;
-#pragma unroll
-                                for (int t = 0; t < RW_TI; ++t) v = (t == t0 + u) ? accd[t] : v;
-                                v_ref[u] = v + (double)ext_own[u];
-                                r_ref[u] = r[u];
-                            }
-                            if ((natural >> s) & 1u) {
-                                t_next = t_next * (1.0 / 64.0);
-                                if (t_next <= a.atol) t_next = 0.0;
-                            }
+                        if (owner && (s >> 2) == my_half) {
+                            const int i = s & 3;
+                            sVref[i * RW_THREADS] = mine + (double)sExt[i * RW_THREADS];
+                            sRref[i * RW_THREADS] = sR[i * RW_THREADS];
+                            if ((natural >> s) & 1u) levels += 1u << (4 * i);      // next rung of the ladder
                         }
                         // r - r_ref is now zero for this stimulus on every row of every CTA
-                        float *col = Xf + (size_t)((buf * 2 + (s >> 2)) * kpad) * 4 + (s & 3);
-                        for (int j = tid; j < kpad; j += RW_THREADS) col[4 * j] = 0.f;
+                        float *col = reinterpret_cast<float *>(smem + L.x_off + buf * RW_BUF_BYTES) + (s & 3);
+                        for (int q = tid; q < MAX_CLUSTER * RW_WARPS * RW_TI; q += RW_THREADS) {
+                            const int blk = q / RW_TI, t = q - blk * RW_TI;
+                            col[4 * (blk * RW_BLK_SLOTS + t + RW_TI * (s >> 2))] = 0.f;
+                        }
                     }
                     __syncthreads();
                 }
@@ -350,10 +392,11 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
 #pragma unroll
                     for (int b = 0; b < TB; ++b) acc[t][b] = 0.f;
                 {
-                    const float4 *Xa = X4 + (buf * 2) * kpad + lane, *Xb = Xa + kpad;
+                    const float4 *Xq = reinterpret_cast<const float4 *>(smem + L.x_off + buf * RW_BUF_BYTES);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
-                        const float4 xa = Xa[c * 32], xb = Xb[c * 32];
+                        const unsigned slot = (c & 1) ? (colslot[c / 2] >> 16) : (colslot[c / 2] & 0xffffu);
+                        const float4 xa = Xq[slot], xb = Xq[slot + RW_TI];
 #pragma unroll
                         for (int t = 0; t < RW_TI; ++t) {
                             const float wq = wreg[t][c];
@@ -368,107 +411,101 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                         }
                     }
                 }
-                // ---- 32-lane reduce-scatter: stimuli over lane bits 4,3,2; rows over bits 1,0 ----
-                float dv[2];
+                // ---- 32-lane reduce-scatter: stimulus half over lane bit 4, rows over bits 3,2,1 ----
+                float dv[4];
                 {
                     const unsigned full = 0xffffffffu;
-                    float v4[RW_TI][4], v2[RW_TI][2], v1[RW_TI + 1], w2[2];
-                    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+                    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+                    float h8[8][4];                                    // rows 0..6 (+ a zero row), my half
 #pragma unroll
                     for (int t = 0; t < RW_TI; ++t)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const float send = u16 ? acc[t][c] : acc[t][4 + c];
                             const float keep = u16 ? acc[t][4 + c] : acc[t][c];
-                            v4[t][c] = keep + __shfl_xor_sync(full, send, 16);
+                            h8[t][c] = keep + __shfl_xor_sync(full, send, 16);
                         }
 #pragma unroll
-                    for (int t = 0; t < RW_TI; ++t)
+                    for (int c = 0; c < 4; ++c) h8[7][c] = 0.f;
+                    float h4[4][4], h2[2][4];
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const float send = u8 ? v4[t][c] : v4[t][2 + c];
-                            const float keep = u8 ? v4[t][2 + c] : v4[t][c];
-                            v2[t][c] = keep + __shfl_xor_sync(full, send, 8);
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float send = u8 ? h8[t][c] : h8[4 + t][c];
+                            const float keep = u8 ? h8[4 + t][c] : h8[t][c];
+                            h4[t][c] = (t == 3 && false) ? keep : keep + __shfl_xor_sync(full, send, 8);
                         }
 #pragma unroll
-                    for (int t = 0; t < RW_TI; ++t) {
-                        const float send = u4 ? v2[t][0] : v2[t][1];
-                        const float keep = u4 ? v2[t][1] : v2[t][0];
-                        v1[t] = keep + __shfl_xor_sync(full, send, 4);
-                    }
-                    v1[RW_TI] = 0.f;
-                    float q4[4];                                   // rows {0..3} or {4..6,-}
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float send = u4 ? h4[t][c] : h4[2 + t][c];
+                            const float keep = u4 ? h4[2 + t][c] : h4[t][c];
+                            h2[t][c] = keep + __shfl_xor_sync(full, send, 4);
+                        }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float send = u2 ? v1[c] : v1[4 + c];
-                        const float keep = u2 ? v1[4 + c] : v1[c];
-                        q4[c] = keep + __shfl_xor_sync(full, send, 2);
+                        const float send = u2 ? h2[0][c] : h2[1][c];
+                        const float keep = u2 ? h2[1][c] : h2[0][c];
+                        const float v = keep + __shfl_xor_sync(full, send, 2);
+                        dv[c] = v + __shfl_xor_sync(full, v, 1);
                     }
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const float send = u1 ? q4[c] : q4[2 + c];
-                        const float keep = u1 ? q4[2 + c] : q4[c];
-                        w2[c] = keep + __shfl_xor_sync(full, send, 1);
-                    }
-                    dv[0] = w2[0]; dv[1] = w2[1];
                 }
-                // stimulus bits: lane bit 4 chose stimuli 4..7, bit 3 the upper pair, bit 2 the odd one
-                // -> stimulus = (bit4 << 2) | (bit3 << 1) | bit2 = lane >> 2  (matches my_stim)
+                // row index: bit 3 chose rows 4..7, bit 2 the upper pair, bit 1 the odd row  -> my_t = (lane >> 1) & 7
 
-                // ---- float64 state update of the (row, stimulus) outputs this lane owns ----
-                const bool frozen = (done >> my_stim) & 1u;
-                bool moving = false, above = false, big = false;
+                // ---- float64 state update of the four outputs an owner lane holds ----
+                unsigned word = 0u;
+                if (owner) {
+                    float xn[4];
 #pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (valid[u]) {
-                        const double v = v_ref[u] + (double)dv[u];
-                        const double fv = io_eval_table(a, tab, v);
-                        const double r_old = r[u];
-                        const double r_new = r_old + (fv - r_old) * (eps_own[u] != 0.f ? a.eps_I : a.eps_E);
-                        if (!frozen && active) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int st = 4 * my_half + i;
+                        const double v = sVref[i * RW_THREADS] + (double)dv[i];
+                        const double fv = (a.dbg & 2) ? v : io_eval_table(a, tab, v);
+                        const double r_old = sR[i * RW_THREADS];
+                        double r_cur = r_old;
+                        const double tl = misc->tlevel[(levels >> (4 * i)) & 7u];
+                        if (!((done >> st) & 1u)) {
+                            const double r_new = r_old + (fv - r_old) * eps_own;
                             const double step = fabs(r_new - r_old);
-                            moving |= step >= a.atol;
-                            big |= step >= t_next;
-                            above |= r_new >= a.r_hard;
-                            r[u] = r_new;
+                            if (step >= a.atol) word |= 1u << st;
+                            if (r_new >= a.r_hard) word |= 1u << (8 + st);
+                            if (step >= tl) word |= 1u << (16 + st);
+                            sR[i * RW_THREADS] = r_new;
+                            r_cur = r_new;
                         }
-                        const unsigned bits = __float_as_uint((float)(r[u] - r_ref[u]));
-                        const unsigned off = xoff[u] + (nbuf ? buf_bytes : 0u);
-#pragma unroll
-                        for (int p = 0; p < MAX_CLUSTER; ++p)
-                            if (p < csize) st_async_u32(x_local + off + pdelta_of(p), bits, full_local[nbuf] + pdelta_of(p));
+                        if (!(tl > 0.0)) word |= 1u << (16 + st);              // ladder exhausted: never request again
+                        xn[i] = (float)(r_cur - sRref[i * RW_THREADS]);
                     }
-                if (!(t_next > 0.0)) big = true;                    // ladder exhausted: never request again
-                {
-                    // per-stimulus OR over the 4 lanes (and all warps, via one word per warp) that own it
-                    unsigned mm = __ballot_sync(0xffffffffu, moving), ma = __ballot_sync(0xffffffffu, above),
-                             mb = __ballot_sync(0xffffffffu, big);
-                    unsigned word = 0u;
-#pragma unroll
-                    for (int s = 0; s < TB; ++s) {
-                        word |= ((mm >> (4 * s)) & 0xfu ? 1u : 0u) << s;
-                        word |= ((ma >> (4 * s)) & 0xfu ? 1u : 0u) << (8 + s);
-                        word |= ((mb >> (4 * s)) & 0xfu ? 1u : 0u) << (16 + s);
-                    }
-                    // a warp without valid rows for a stimulus must not veto: it reports nothing (bits clear)
-                    if (lane == 0) {
-#pragma unroll
-                        for (int p = 0; p < MAX_CLUSTER; ++p)
-                            if (p < csize)
-                                st_async_u32(flag_local + 4u * (unsigned)((nbuf * MAX_CLUSTER + rank) * RW_WARPS + warp) + pdelta_of(p),
-                                             word, full_local[nbuf] + pdelta_of(p));
-                    }
+                    *reinterpret_cast<float4 *>(smem + L.x_off + nbuf * RW_BUF_BYTES + xoff) =
+                        make_float4(xn[0], xn[1], xn[2], xn[3]);
+                }
+                word = __reduce_or_sync(0xffffffffu, word);
+                if (lane == 0)
+                    *reinterpret_cast<unsigned *>(smem + L.x_off + nbuf * RW_BUF_BYTES + my_block + 2 * RW_TI * 16) = word;
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_release(full_local[nbuf]);
+                else if (lane <= csize - 1 && !(a.dbg & 1)) {
+                    const int p = lane - 1 + (lane - 1 >= rank ? 1 : 0);
+                    const unsigned src = x_local + (unsigned)(nbuf * RW_BUF_BYTES) + my_block;
+                    bulk_copy_to_peer(src + pdelta[p], src, RW_BLK_BYTES, full_local[nbuf] + pdelta[p]);
                 }
                 buf = nbuf;
             }
 
             // ---- results ----
+            if (owner) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-                if (valid[u] && active) a.R[sol * dim + grow[u]] = (float)r[u];
-            if (rank == 0 && warp == 0 && (lane & 3) == 0 && active) {
-                a.status[sol] = my_status;
-                if (a.iters) a.iters[sol] = my_iters;
+                for (int i = 0; i < 4; ++i) {
+                    const int st = 4 * my_half + i;
+                    if (st < nact) a.R[((size_t)net * a.nb + b0 + st) * dim + grow] = (float)sR[i * RW_THREADS];
+                }
+            }
+            if (rank == 0 && warp == 0 && lane < nact) {               // lane == sid for lanes 0..7
+                a.status[(size_t)net * a.nb + b0 + lane] = my_status;
+                if (a.iters) a.iters[(size_t)net * a.nb + b0 + lane] = my_iters;
             }
             // nobody may publish the next panel while a slower CTA still reads this one
             cluster.sync();
@@ -572,6 +609,7 @@ int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, i
     a.atol = sv.atol; a.r_hard = sv.rate_hard_bound;
     a.max_iter = sv.max_iter; a.check_hard = sv.io_type != SSN_IO_TANH;
     a.tab_nodes = plan.tab_nodes;
+    a.dbg = getenv("SSN_DBG") ? atoi(getenv("SSN_DBG")) : 0;
     // refresh ladder: thresholds atol * 64^j, starting at the largest one below 0.1
     double t = sv.atol > 0 ? sv.atol : 1e-300;
     while (t * 64.0 < 0.1) t *= 64.0;
