@@ -22,6 +22,7 @@
 // |r_new - r_old| < atol first holds then matches the float64 reference solver
 // (tc_gan/ext/ssnode.c:84-96) instead of jittering by tens of sweeps.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include "ssn_cluster_core.cuh"
 #include "ssn_launch.h"
@@ -54,6 +55,7 @@ struct RwArgs {
     double eps_E, eps_I, atol, r_hard, t_first;        // t_first: first refresh threshold on |dr|
     int max_iter, check_hard, tab_nodes;
     int dbg;                                           // development switches (SSN_DBG), 0 in production
+    long long *dbg_out;                                // phase cycle counters when dbg & 4
 };
 
 struct RwSmem {
@@ -120,6 +122,22 @@ __device__ __forceinline__ void st_async_u32(unsigned addr, unsigned v, unsigned
                  ::"r"(addr), "r"(v), "r"(bar) : "memory");
 }
 
+// packed FP32 pairs (FFMA2): a register pair holds rows (2p, 2p+1) of the W tile / of the accumulators, so one
+// fma.rn.f32x2 with the broadcast x does two FMAs and its operands can never collide on a register bank
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long long w, float x) {
+    unsigned long long xx;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(xx));
+}
+
 // f(v) in float64: cubic expansion around the nearest table node for v in [1, table end],
 // accurate float for v < 1 (|f| < k: absolute error ~1e-9 k), closed form above the table.
 __device__ __forceinline__ double io_eval_table(const RwArgs &a, const double *tab, double v) {
@@ -162,10 +180,12 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
     const int row0 = warp * RW_TI;                                  // first local row of this warp
 
     // ownership after the 32-lane reduce-scatter: lane bit 4 -> stimulus half h (stimuli 4h..4h+3),
-    // bits 3..1 -> row t of the warp's seven; the even lane of each pair is the owner.
+    // bits 3..1 -> row t of the warp's seven, bit 0 -> which two of the four stimuli of the half.
     const int my_half = lane >> 4;
     const int my_t = (lane >> 1) & 7;
-    const bool owner = ((lane & 1) == 0) && my_t < RW_TI && (row0 + my_t < rows_here);
+    const int my_pair = lane & 1;
+    const int my_st0 = 4 * my_half + 2 * my_pair;                   // my stimuli: my_st0, my_st0 + 1
+    const bool owner = my_t < RW_TI && (row0 + my_t < rows_here);
     const int grow = row_base + row0 + my_t;                        // global row of the owned outputs
     const int sid = lane & 7;                                       // stimulus whose status this lane tracks
 
@@ -230,23 +250,28 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
         if (net >= a.nz) break;
 
         // ---- W tile -> registers ----
-        float wreg[RW_TI][NC];
+        unsigned long long wp[3][NC];                              // rows (0,1), (2,3), (4,5) as packed pairs
+        float ws[NC];                                              // row 6
         {
             const float *src = a.w + (size_t)net * dim * dim;
 #pragma unroll
-            for (int t = 0; t < RW_TI; ++t) {
-                const int i = row_base + row0 + t;
-                const bool rv = row0 + t < rows_here;
+            for (int c = 0; c < NC; ++c) {
+                const int j = c * 32 + lane;
+                float wv[RW_TI];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const int j = c * 32 + lane;
+                for (int t = 0; t < RW_TI; ++t) {
+                    const int i = row_base + row0 + t;
                     float v = 0.f;
-                    if (rv && j < dim) {
+                    if (row0 + t < rows_here && j < dim) {
                         v = __ldg(src + (size_t)i * dim + j);
                         if (a.w_kind == SSN_W_FROM_Z) v = weight_from_z(a.wc, gtab, N, i, j, v);
                     }
-                    wreg[t][c] = v;
+                    wv[t] = v;
                 }
+                wp[0][c] = pack2(wv[0], wv[1]);
+                wp[1][c] = pack2(wv[2], wv[3]);
+                wp[2][c] = pack2(wv[4], wv[5]);
+                ws[c] = wv[6];
             }
         }
 
@@ -257,22 +282,22 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
 
             // float64 state of the four (row, stimulus) outputs an owner lane holds lives in shared memory
             const double eps_own = grow < N ? a.eps_E : a.eps_I;
-            unsigned levels = 0u;                            // refresh-ladder level of my four stimuli, 4 bits each
-            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned levels = 0u;                            // refresh-ladder level of my two stimuli, 4 bits each
+            float x0[2] = {0.f, 0.f};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
                 double r0 = 0.0;
                 float e = 0.f;
-                const int st = 4 * my_half + i;
+                const int st = my_st0 + i;
                 if (owner && st < nact) {
                     e = __ldg(ext_net + (size_t)(b0 + st) * dim + grow);
                     if (a.r_init) r0 = (double)__ldg(a.r_init + ((size_t)net * a.nb + b0 + st) * dim + grow);
                 }
                 sR[i * RW_THREADS] = r0; sRref[i * RW_THREADS] = 0.0; sVref[i * RW_THREADS] = (double)e;
                 sExt[i * RW_THREADS] = e;
-                (&x0.x)[i] = (float)r0;
+                x0[i] = (float)r0;
             }
-            const unsigned xoff = my_block + 16u * (unsigned)(my_t + RW_TI * my_half);   // my float4 inside a buffer
+            const unsigned xoff = my_block + 16u * (unsigned)(my_t + RW_TI * my_half) + 8u * (unsigned)my_pair;   // my float2
             unsigned done = nact >= TB ? 0u : (0xffu << nact) & 0xffu;
             unsigned force_refresh = a.r_init ? (~done & 0xffu) : 0u;   // with r_init the first sweep refreshes
             int my_status = 1, my_iters = a.max_iter;                   // of stimulus `sid`
@@ -280,7 +305,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
             // ---- publish the initial panel: r - r_ref (= r_init, refreshed at once, or 0) ----
             int buf = 0;
             if (tid == 0) mbar_arrive_expect_tx(full_local[0], tx_bytes);
-            if (owner) *reinterpret_cast<float4 *>(smem + L.x_off + xoff) = x0;
+            if (owner) *reinterpret_cast<float2 *>(smem + L.x_off + xoff) = make_float2(x0[0], x0[1]);
             if (lane == 0)
                 *reinterpret_cast<unsigned *>(smem + L.x_off + my_block + 2 * RW_TI * 16) = 0x00ff0000u;  // "big": no refresh yet
             fence_proxy_async();
@@ -292,9 +317,12 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                                   full_local[0] + pdelta[p]);
             }
 
+            long long tc[6] = {0, 0, 0, 0, 0, 0};
             for (int it = 1;; ++it) {
+                long long c0 = clock64();
                 // ---- wait for the panel of this sweep and the flags of the previous one ----
                 mbar_wait(full_local[buf], ph[buf]);
+                long long c1 = clock64(); tc[0] += c1 - c0;
                 ph[buf] ^= 1u;
                 unsigned F;
                 {
@@ -322,8 +350,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                     if (tid == 0) mbar_arrive_expect_tx(xfull_local, nreq * (unsigned)dim * 8u);
                     if (owner) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int st = 4 * my_half + i;
+                        for (int i = 0; i < 2; ++i) {
+                            const int st = my_st0 + i;
                             if ((req >> st) & 1u) {
                                 const double ri = sR[i * RW_THREADS];
                                 const float hi = (float)ri;
@@ -353,10 +381,15 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                         for (int c = 0; c < NC; ++c) {
                             const double h = (double)xh[c * 32 + lane];
                             const float l = xl[c * 32 + lane];
+                            float wv[RW_TI];
+                            unpack2(wp[0][c], wv[0], wv[1]);
+                            unpack2(wp[1][c], wv[2], wv[3]);
+                            unpack2(wp[2][c], wv[4], wv[5]);
+                            wv[6] = ws[c];
 #pragma unroll
                             for (int t = 0; t < RW_TI; ++t) {
-                                accd[t] = fma((double)wreg[t][c], h, accd[t]);     // exact products, fp64 sum
-                                accf[t] = fmaf(wreg[t][c], l, accf[t]);
+                                accd[t] = fma((double)wv[t], h, accd[t]);          // exact products, fp64 sum
+                                accf[t] = fmaf(wv[t], l, accf[t]);
                             }
                         }
                         double mine = 0.0;
@@ -367,8 +400,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                             mine = (t == my_t) ? v : mine;
                         }
-                        if (owner && (s >> 2) == my_half) {
-                            const int i = s & 3;
+                        if (owner && (s >> 1) == (my_st0 >> 1)) {
+                            const int i = s & 1;
                             sVref[i * RW_THREADS] = mine + (double)sExt[i * RW_THREADS];
                             sRref[i * RW_THREADS] = sR[i * RW_THREADS];
                             if ((natural >> s) & 1u) levels += 1u << (4 * i);      // next rung of the ladder
@@ -385,37 +418,42 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
 
                 // ---- arm the next phase, then contract: dv = W * fl32(r - r_ref) ----
                 const int nbuf = buf ^ 1;
+                long long c2 = clock64(); tc[1] += c2 - c1;
                 if (tid == 0) mbar_arrive_expect_tx(full_local[nbuf], tx_bytes);
                 float acc[RW_TI][TB];
-#pragma unroll
-                for (int t = 0; t < RW_TI; ++t)
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) acc[t][b] = 0.f;
                 {
+                    unsigned long long ap[3][TB];
+                    float as[TB];
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) { ap[0][b] = 0ull; ap[1][b] = 0ull; ap[2][b] = 0ull; as[b] = 0.f; }
                     const float4 *Xq = reinterpret_cast<const float4 *>(smem + L.x_off + buf * RW_BUF_BYTES);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         const unsigned slot = (c & 1) ? (colslot[c / 2] >> 16) : (colslot[c / 2] & 0xffffu);
                         const float4 xa = Xq[slot], xb = Xq[slot + RW_TI];
+                        const float xv[TB] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                        for (int t = 0; t < RW_TI; ++t) {
-                            const float wq = wreg[t][c];
-                            acc[t][0] = fmaf(wq, xa.x, acc[t][0]);
-                            acc[t][1] = fmaf(wq, xa.y, acc[t][1]);
-                            acc[t][2] = fmaf(wq, xa.z, acc[t][2]);
-                            acc[t][3] = fmaf(wq, xa.w, acc[t][3]);
-                            acc[t][4] = fmaf(wq, xb.x, acc[t][4]);
-                            acc[t][5] = fmaf(wq, xb.y, acc[t][5]);
-                            acc[t][6] = fmaf(wq, xb.z, acc[t][6]);
-                            acc[t][7] = fmaf(wq, xb.w, acc[t][7]);
+                        for (int b = 0; b < TB; ++b) {
+                            ffma2(ap[0][b], wp[0][c], xv[b]);
+                            ffma2(ap[1][b], wp[1][c], xv[b]);
+                            ffma2(ap[2][b], wp[2][c], xv[b]);
+                            as[b] = fmaf(ws[c], xv[b], as[b]);
                         }
                     }
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) {
+                        unpack2(ap[0][b], acc[0][b], acc[1][b]);
+                        unpack2(ap[1][b], acc[2][b], acc[3][b]);
+                        unpack2(ap[2][b], acc[4][b], acc[5][b]);
+                        acc[6][b] = as[b];
+                    }
                 }
-                // ---- 32-lane reduce-scatter: stimulus half over lane bit 4, rows over bits 3,2,1 ----
-                float dv[4];
+                long long c3 = clock64(); tc[2] += c3 - c2;
+                // ---- 32-lane reduce-scatter: stimulus half over lane bit 4, rows over bits 3,2,1, stimulus pair over bit 0 ----
+                float dv[2];
                 {
                     const unsigned full = 0xffffffffu;
-                    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+                    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
                     float h8[8][4];                                    // rows 0..6 (+ a zero row), my half
 #pragma unroll
                     for (int t = 0; t < RW_TI; ++t)
@@ -427,14 +465,14 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                         }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) h8[7][c] = 0.f;
-                    float h4[4][4], h2[2][4];
+                    float h4[4][4], h2[2][4], h1[4];
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const float send = u8 ? h8[t][c] : h8[4 + t][c];
                             const float keep = u8 ? h8[4 + t][c] : h8[t][c];
-                            h4[t][c] = (t == 3 && false) ? keep : keep + __shfl_xor_sync(full, send, 8);
+                            h4[t][c] = keep + __shfl_xor_sync(full, send, 8);
                         }
 #pragma unroll
                     for (int t = 0; t < 2; ++t)
@@ -448,19 +486,25 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                     for (int c = 0; c < 4; ++c) {
                         const float send = u2 ? h2[0][c] : h2[1][c];
                         const float keep = u2 ? h2[1][c] : h2[0][c];
-                        const float v = keep + __shfl_xor_sync(full, send, 2);
-                        dv[c] = v + __shfl_xor_sync(full, v, 1);
+                        h1[c] = keep + __shfl_xor_sync(full, send, 2);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float send = u1 ? h1[c] : h1[2 + c];
+                        const float keep = u1 ? h1[2 + c] : h1[c];
+                        dv[c] = keep + __shfl_xor_sync(full, send, 1);
                     }
                 }
                 // row index: bit 3 chose rows 4..7, bit 2 the upper pair, bit 1 the odd row  -> my_t = (lane >> 1) & 7
 
-                // ---- float64 state update of the four outputs an owner lane holds ----
+                long long c4 = clock64(); tc[3] += c4 - c3;
+                // ---- float64 state update of the two outputs this lane owns ----
                 unsigned word = 0u;
                 if (owner) {
-                    float xn[4];
+                    float xn[2];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int st = 4 * my_half + i;
+                    for (int i = 0; i < 2; ++i) {
+                        const int st = my_st0 + i;
                         const double v = sVref[i * RW_THREADS] + (double)dv[i];
                         const double fv = (a.dbg & 2) ? v : io_eval_table(a, tab, v);
                         const double r_old = sR[i * RW_THREADS];
@@ -478,9 +522,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                         if (!(tl > 0.0)) word |= 1u << (16 + st);              // ladder exhausted: never request again
                         xn[i] = (float)(r_cur - sRref[i * RW_THREADS]);
                     }
-                    *reinterpret_cast<float4 *>(smem + L.x_off + nbuf * RW_BUF_BYTES + xoff) =
-                        make_float4(xn[0], xn[1], xn[2], xn[3]);
+                    *reinterpret_cast<float2 *>(smem + L.x_off + nbuf * RW_BUF_BYTES + xoff) = make_float2(xn[0], xn[1]);
                 }
+                long long c5 = clock64(); tc[4] += c5 - c4;
                 word = __reduce_or_sync(0xffffffffu, word);
                 if (lane == 0)
                     *reinterpret_cast<unsigned *>(smem + L.x_off + nbuf * RW_BUF_BYTES + my_block + 2 * RW_TI * 16) = word;
@@ -493,13 +537,16 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                     bulk_copy_to_peer(src + pdelta[p], src, RW_BLK_BYTES, full_local[nbuf] + pdelta[p]);
                 }
                 buf = nbuf;
+                tc[5] += clock64() - c5;
             }
+            if ((a.dbg & 4) && a.dbg_out && net == 0 && tid == 0)
+                for (int q = 0; q < 6; ++q) a.dbg_out[rank * 6 + q] = tc[q];
 
             // ---- results ----
             if (owner) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int st = 4 * my_half + i;
+                for (int i = 0; i < 2; ++i) {
+                    const int st = my_st0 + i;
                     if (st < nact) a.R[((size_t)net * a.nb + b0 + st) * dim + grow] = (float)sR[i * RW_THREADS];
                 }
             }
@@ -628,8 +675,21 @@ int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, i
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (a.dbg & 4) SSN_CUDA(cudaMalloc(&a.dbg_out, 64 * sizeof(long long)));
     SSN_CUDA(cudaLaunchKernelEx(&cfg, plan.fn, a));
     count_launch();
+    if (a.dbg & 4) {
+        long long h[48];
+        SSN_CUDA(cudaStreamSynchronize(stream));
+        SSN_CUDA(cudaMemcpy(h, a.dbg_out, sizeof(h), cudaMemcpyDeviceToHost));
+        const char *names[6] = {"wait", "top/refresh", "contract", "reduce", "update", "publish"};
+        for (int r = 0; r < plan.csize; r += plan.csize - 1 > 0 ? plan.csize - 1 : 1) {
+            fprintf(stderr, "[ssn dbg] rank %d cycles (net 0, all sweeps):", r);
+            for (int q = 0; q < 6; ++q) fprintf(stderr, " %s=%lld", names[q], h[r * 6 + q]);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(a.dbg_out);
+    }
     return 0;
 }
 
