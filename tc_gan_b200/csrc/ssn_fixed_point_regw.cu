@@ -29,14 +29,17 @@
 
 namespace ssn {
 
-constexpr int RW_TI = 7, RW_WARPS = 8, RW_THREADS = 256, RW_ROWS = RW_TI * RW_WARPS;
+constexpr int RW_TI = 7;                               // rows per warp
+constexpr int RW_MAXC = 16;                            // largest cluster (non-portable size, 4-warp CTAs)
+constexpr int RW_BLOCKS = 64;                          // csize * warps <= 64 panel blocks
+constexpr int RW_XE = 4;                               // stimuli refreshed per event
 // State panel: one block per (source CTA, warp): 7 float4 rows of stimuli 0..3, 7 float4 rows of
 // stimuli 4..7, one 16-byte slot whose first word carries the warp's flags.  A warp publishes its
 // block to a peer CTA with ONE cp.async.bulk (one mbarrier transaction per block, not per element).
 constexpr int RW_BLK_SLOTS = 2 * RW_TI + 1, RW_BLK_BYTES = RW_BLK_SLOTS * 16;          // 15 slots, 240 B
-constexpr int RW_ZERO_SLOT = MAX_CLUSTER * RW_WARPS * RW_BLK_SLOTS;                     // slot 960: always 0
+constexpr int RW_ZERO_SLOT = RW_BLOCKS * RW_BLK_SLOTS;                                  // slot 960: always 0
 constexpr int RW_BUF_BYTES = (RW_ZERO_SLOT + 1) * 16;
-constexpr int TAB_PER_UNIT = 16;                       // table nodes per unit of v
+constexpr int TAB_PER_UNIT = 8;                        // table nodes per unit of v
 constexpr double TAB_V_MIN = 1.0;
 
 struct RwArgs {
@@ -62,22 +65,22 @@ struct RwSmem {
     int x_off, xe_off, tab_off, gtab_off, state_off, misc_off, total;
 };
 // per-thread float64 state of the owner lanes, kept in shared memory so that the sweep loop's
-// registers hold only the W tile and the accumulators: r, r_ref, v_ref as [4][256] doubles, ext as [4][256] floats
-constexpr int RW_STATE_BYTES = 3 * 4 * RW_THREADS * 8 + 4 * RW_THREADS * 4;
+// registers hold only the W tile and the accumulators: r, r_ref, v_ref as [2][threads] doubles, ext as [2][threads] floats
+__host__ __device__ constexpr int rw_state_bytes(int nt) { return 3 * 2 * nt * 8 + 2 * nt * 4; }
 struct RwMisc {
     unsigned long long full[2], xfull;
     double tlevel[8];                        // refresh ladder: thresholds on max|dr| by level, 0 = exhausted
-    unsigned pdelta[MAX_CLUSTER];
+    unsigned pdelta[RW_MAXC];
     int next_net;
 };
-__host__ __device__ inline RwSmem rw_smem_layout(int kpad, int n_sites, int tab_nodes) {
+__host__ __device__ inline RwSmem rw_smem_layout(int kpad, int n_sites, int tab_nodes, int nt) {
     RwSmem L;
     int o = 0;
     L.x_off = o;    o += 2 * RW_BUF_BYTES;             // [buf][source CTA][warp] blocks of RW_BLK_BYTES + a zero slot
-    L.xe_off = o;   o += 2 * TB * kpad * 4;            // exact-pass columns: hi[8][kpad], lo[8][kpad]
+    L.xe_off = o;   o += 2 * RW_XE * kpad * 4;         // exact-pass columns: hi[4][kpad], lo[4][kpad]
     L.tab_off = o;  o += tab_nodes * 32;               // cubic table of f: 4 doubles per node
     L.gtab_off = o; o += ((4 * n_sites * 4 + 15) / 16) * 16;
-    L.state_off = o; o += RW_STATE_BYTES;
+    L.state_off = o; o += rw_state_bytes(nt);
     L.misc_off = o; o += 1024;
     L.total = o;
     return L;
@@ -158,21 +161,22 @@ __device__ __forceinline__ double io_eval_table(const RwArgs &a, const double *t
     return a.io.k * pow(v, a.io.n);                     // beyond the table (diverging power-law network)
 }
 
-template <int NC>
-__global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs a) {
+template <int NC, int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(const RwArgs a) {
+    constexpr int RW_WARPS = NW, RW_THREADS = 32 * NW;
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int csize = a.csize, dim = a.dim, kpad = a.kpad, rpc = a.rpc, N = a.n_sites;
-    const RwSmem L = rw_smem_layout(kpad, N, a.tab_nodes);
+    const RwSmem L = rw_smem_layout(kpad, N, a.tab_nodes, RW_THREADS);
     float *Xf = reinterpret_cast<float *>(smem + L.x_off);
     float *xe = reinterpret_cast<float *>(smem + L.xe_off);
     double *tab = reinterpret_cast<double *>(smem + L.tab_off);
     float *gtab = reinterpret_cast<float *>(smem + L.gtab_off);
     RwMisc *misc = reinterpret_cast<RwMisc *>(smem + L.misc_off);
     double *sR = reinterpret_cast<double *>(smem + L.state_off) + threadIdx.x;        // [i][256]
-    double *sRref = sR + 4 * RW_THREADS, *sVref = sR + 8 * RW_THREADS;
-    float *sExt = reinterpret_cast<float *>(smem + L.state_off + 3 * 4 * RW_THREADS * 8) + threadIdx.x;
+    double *sRref = sR + 2 * RW_THREADS, *sVref = sR + 4 * RW_THREADS;
+    float *sExt = reinterpret_cast<float *>(smem + L.state_off + 3 * 2 * RW_THREADS * 8) + threadIdx.x;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_base = rank * rpc;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
     const unsigned xfull_local = smem_u32(&misc->xfull);
     // shared::cluster address of the same offset in CTA p = local address + pdelta[p]
     // (the cluster window of every CTA is laid out identically, so one subtraction gives the offset)
-    if (tid < MAX_CLUSTER) misc->pdelta[tid] = map_to_rank(x_local, (unsigned)(tid < csize ? tid : 0)) - x_local;
+    if (tid < RW_MAXC) misc->pdelta[tid] = map_to_rank(x_local, (unsigned)(tid < csize ? tid : 0)) - x_local;
     const volatile unsigned *pdelta = misc->pdelta;
 
     // ---- one-time setup ----
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 2 * RW_BUF_BYTES / 4; i += RW_THREADS) Xf[i] = 0.f;
-    for (int i = tid; i < 2 * TB * kpad; i += RW_THREADS) xe[i] = 0.f;
+    for (int i = tid; i < 2 * RW_XE * kpad; i += RW_THREADS) xe[i] = 0.f;
     if (a.w_kind == SSN_W_FROM_Z) build_profile_table(a.wc, N, gtab, tid, RW_THREADS);
     for (int i = tid; i < a.tab_nodes; i += RW_THREADS) {           // cubic table of k v^n
         const double v = TAB_V_MIN + (double)i / TAB_PER_UNIT, h = 1.0 / TAB_PER_UNIT;
@@ -343,8 +347,14 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
 
                 // ---- reference-point refresh for stimuli whose max|dr| fell below their ladder threshold ----
                 const unsigned natural = ~(F >> 16) & ~done & 0xffu;
-                const unsigned req = natural | (force_refresh & ~done);
-                force_refresh = 0u;
+                unsigned req = natural | (force_refresh & ~done);
+                {
+                    // at most RW_XE stimuli per event; the rest keep asking and are served on the next sweeps
+                    unsigned keep = 0u, left = req;
+                    for (int q = 0; q < RW_XE && left; ++q) { keep |= left & (0u - left); left &= left - 1u; }
+                    force_refresh &= ~keep;
+                    req = keep;
+                }
                 if (req) {
                     const unsigned nreq = __popc(req);
                     if (tid == 0) mbar_arrive_expect_tx(xfull_local, nreq * (unsigned)dim * 8u);
@@ -356,15 +366,15 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                                 const double ri = sR[i * RW_THREADS];
                                 const float hi = (float)ri;
                                 const float lo = (float)(ri - (double)hi);
-                                const unsigned o = 4u * (unsigned)(st * kpad + grow);
-#pragma unroll
-                                for (int p = 0; p < MAX_CLUSTER; ++p)
-                                    if (p < csize) {
+                                const unsigned o = 4u * (unsigned)(__popc(req & ((1u << st) - 1u)) * kpad + grow);
+                                for (int p = 0; p < csize; ++p) {
+                                    {
                                         const unsigned bar = xfull_local + pdelta[p];
                                         st_async_u32(xe_local + o + pdelta[p], __float_as_uint(hi), bar);
-                                        st_async_u32(xe_local + o + 4u * (unsigned)(TB * kpad) + pdelta[p],
+                                        st_async_u32(xe_local + o + 4u * (unsigned)(RW_XE * kpad) + pdelta[p],
                                                      __float_as_uint(lo), bar);
                                     }
+                                }
                             }
                         }
                     }
@@ -372,7 +382,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                     xph ^= 1u;
                     for (int s = 0; s < TB; ++s) {
                         if (!((req >> s) & 1u)) continue;
-                        const float *xh = xe + s * kpad, *xl = xe + (TB + s) * kpad;
+                        const int xs = __popc(req & ((1u << s) - 1u));
+                        const float *xh = xe + xs * kpad, *xl = xe + (RW_XE + xs) * kpad;
                         double accd[RW_TI];
                         float accf[RW_TI];
 #pragma unroll
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
                         }
                         // r - r_ref is now zero for this stimulus on every row of every CTA
                         float *col = reinterpret_cast<float *>(smem + L.x_off + buf * RW_BUF_BYTES) + (s & 3);
-                        for (int q = tid; q < MAX_CLUSTER * RW_WARPS * RW_TI; q += RW_THREADS) {
+                        for (int q = tid; q < RW_BLOCKS * RW_TI; q += RW_THREADS) {
                             const int blk = q / RW_TI, t = q - blk * RW_TI;
                             col[4 * (blk * RW_BLK_SLOTS + t + RW_TI * (s >> 2))] = 0.f;
                         }
@@ -564,13 +575,23 @@ __global__ void __launch_bounds__(RW_THREADS, 1) ssn_fp_regw_kernel(const RwArgs
 // host side
 // ------------------------------------------------------------------------------------
 typedef void (*RwKernel)(const RwArgs);
-static RwKernel pick_rw_kernel(int nc) {
+static RwKernel pick_rw_kernel(int nc, int nw) {
+    if (nw == 4) {
+        switch (nc) {
+            case 2: return ssn_fp_regw_kernel<2, 4>;
+            case 4: return ssn_fp_regw_kernel<4, 4>;
+            case 7: return ssn_fp_regw_kernel<7, 4>;
+            case 10: return ssn_fp_regw_kernel<10, 4>;
+            case 14: return ssn_fp_regw_kernel<14, 4>;
+        }
+        return nullptr;
+    }
     switch (nc) {
-        case 2: return ssn_fp_regw_kernel<2>;
-        case 4: return ssn_fp_regw_kernel<4>;
-        case 7: return ssn_fp_regw_kernel<7>;
-        case 10: return ssn_fp_regw_kernel<10>;
-        case 14: return ssn_fp_regw_kernel<14>;
+        case 2: return ssn_fp_regw_kernel<2, 8>;
+        case 4: return ssn_fp_regw_kernel<4, 8>;
+        case 7: return ssn_fp_regw_kernel<7, 8>;
+        case 10: return ssn_fp_regw_kernel<10, 8>;
+        case 14: return ssn_fp_regw_kernel<14, 8>;
     }
     return nullptr;
 }
@@ -582,15 +603,16 @@ static int rw_nc_for(int dim) {
     return 0;
 }
 
-struct RwPlan { RwKernel fn; int nc, kpad, csize, rpc, smem, clusters, tab_nodes; };
+struct RwPlan { RwKernel fn; int nc, nw, kpad, csize, rpc, smem, clusters, tab_nodes; };
 
-static int plan_regw(const ssn_solver &sv, int n_sites, int nz, RwPlan *plan) {
-    const int dim = 2 * n_sites;
+static int plan_regw_nw(const ssn_solver &sv, int n_sites, int nz, int nw, RwPlan *plan) {
+    const int dim = 2 * n_sites, rows = RW_TI * nw;
+    plan->nw = nw;
     plan->nc = rw_nc_for(dim);
     if (!plan->nc) return 1;                                   // too large: caller falls back to the smem kernel
     plan->kpad = 32 * plan->nc;
-    plan->csize = (dim + RW_ROWS - 1) / RW_ROWS;
-    if (plan->csize > MAX_CLUSTER) return 1;
+    plan->csize = (dim + rows - 1) / rows;
+    if (plan->csize > (nw == 4 ? RW_MAXC : MAX_CLUSTER) || plan->csize * nw > RW_BLOCKS) return 1;
     plan->rpc = (dim + plan->csize - 1) / plan->csize;
     if (plan->rpc * (plan->csize - 1) >= dim) return 1;
     // table of k v^n on [1, min(v0, 160)] (power type: to 160, beyond it the closed form is used)
@@ -598,13 +620,14 @@ static int plan_regw(const ssn_solver &sv, int n_sites, int nz, RwPlan *plan) {
     double v_end = (sv.io_type == SSN_IO_POWER || !(v0 < 160.0)) ? 160.0 : v0 + 1.0;
     if (!(v_end > 2.0)) v_end = 2.0;
     plan->tab_nodes = (int)((v_end - TAB_V_MIN) * TAB_PER_UNIT) + 2;
-    plan->smem = rw_smem_layout(plan->kpad, n_sites, plan->tab_nodes).total;
+    plan->smem = rw_smem_layout(plan->kpad, n_sites, plan->tab_nodes, 32 * nw).total;
     int dev = 0, limit = 0;
     SSN_CUDA(cudaGetDevice(&dev));
     SSN_CUDA(cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (plan->smem > limit) return 1;
-    plan->fn = pick_rw_kernel(plan->nc);
+    plan->fn = pick_rw_kernel(plan->nc, nw);
     SSN_CUDA(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem));
+    if (plan->csize > 8) SSN_CUDA(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -612,15 +635,25 @@ static int plan_regw(const ssn_solver &sv, int n_sites, int nz, RwPlan *plan) {
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(plan->csize, 1, 1);
-    cfg.blockDim = dim3(RW_THREADS, 1, 1);
+    cfg.blockDim = dim3(32 * nw, 1, 1);
     cfg.dynamicSmemBytes = plan->smem;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int max_clusters = 0;
-    SSN_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, plan->fn, &cfg));
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, plan->fn, &cfg) != cudaSuccess) { cudaGetLastError(); return 1; }
     if (max_clusters < 1) return 1;
     plan->clusters = nz > 0 ? std::min(max_clusters, nz) : max_clusters;
     return 0;
+}
+
+// 4-warp CTAs (two co-resident per SM, from different networks, so one network's epilogue and
+// exchange hide under another's contraction) when that shape is schedulable; else 8-warp CTAs.
+static int plan_regw(const ssn_solver &sv, int n_sites, int nz, RwPlan *plan) {
+    const char *force = getenv("SSN_REGW_WARPS");
+    const int first = force ? atoi(force) : 4;
+    int rc = plan_regw_nw(sv, n_sites, nz, first == 8 ? 8 : 4, plan);
+    if (rc == 1 && !force) rc = plan_regw_nw(sv, n_sites, nz, 8, plan);
+    return rc;
 }
 
 int regw_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *resident_clusters) {
@@ -670,12 +703,12 @@ int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, i
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(plan.clusters * plan.csize, 1, 1);
-    cfg.blockDim = dim3(RW_THREADS, 1, 1);
+    cfg.blockDim = dim3(32 * plan.nw, 1, 1);
     cfg.dynamicSmemBytes = plan.smem;
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (a.dbg & 4) SSN_CUDA(cudaMalloc(&a.dbg_out, 64 * sizeof(long long)));
+    if (a.dbg & 4) SSN_CUDA(cudaMalloc(&a.dbg_out, 128 * sizeof(long long)));
     SSN_CUDA(cudaLaunchKernelEx(&cfg, plan.fn, a));
     count_launch();
     if (a.dbg & 4) {
@@ -683,7 +716,8 @@ int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, i
         SSN_CUDA(cudaStreamSynchronize(stream));
         SSN_CUDA(cudaMemcpy(h, a.dbg_out, sizeof(h), cudaMemcpyDeviceToHost));
         const char *names[6] = {"wait", "top/refresh", "contract", "reduce", "update", "publish"};
-        for (int r = 0; r < plan.csize; r += plan.csize - 1 > 0 ? plan.csize - 1 : 1) {
+        fprintf(stderr, "[ssn dbg] warps/CTA %d cluster %d resident clusters %d smem %d\n", plan.nw, plan.csize, plan.clusters, plan.smem);
+        for (int r = 0; r < (plan.csize < 8 ? plan.csize : 8); r += 7) {
             fprintf(stderr, "[ssn dbg] rank %d cycles (net 0, all sweeps):", r);
             for (int q = 0; q < 6; ++q) fprintf(stderr, " %s=%lld", names[q], h[r * 6 + q]);
             fprintf(stderr, "\n");
