@@ -646,13 +646,13 @@ static int plan_regw_nw(const ssn_solver &sv, int n_sites, int nz, int nw, RwPla
     return 0;
 }
 
-// 4-warp CTAs (two co-resident per SM, from different networks, so one network's epilogue and
-// exchange hide under another's contraction) when that shape is schedulable; else 8-warp CTAs.
+// 8-warp CTAs in portable clusters (<= 8) by default; SSN_REGW_WARPS=4 selects 4-warp CTAs (two
+// co-resident per SM, clusters of up to 16): measured equal in throughput at 2N = 402 on B200.
 static int plan_regw(const ssn_solver &sv, int n_sites, int nz, RwPlan *plan) {
     const char *force = getenv("SSN_REGW_WARPS");
-    const int first = force ? atoi(force) : 4;
+    const int first = force ? atoi(force) : 8;
     int rc = plan_regw_nw(sv, n_sites, nz, first == 8 ? 8 : 4, plan);
-    if (rc == 1 && !force) rc = plan_regw_nw(sv, n_sites, nz, 8, plan);
+    if (rc == 1 && !force) rc = plan_regw_nw(sv, n_sites, nz, 4, plan);
     return rc;
 }
 
