@@ -1,14 +1,19 @@
 """
 GPU parity tests of the fixed-point path (K1) through the C ABI.
 
-Tolerance of the fast path (FP32 FFMA contraction, float64 state): rtol 1e-4 as
-BASELINE.json's north_star states, with the atol floor the reference's own
-cross-solver tests use (tc_gan/networks/tests/test_euler_ssn.py:36,86), because
-the reference stops as soon as one Euler step moves every rate by < atol=1e-5,
-i.e. within ~1e-3 of the true fixed point: a solver that stops a few sweeps
-earlier or later differs by (sweeps x 1e-5).  The float64 path must agree to
-1e-10 with identical sweep counts.
+Tolerances.  The reference stops as soon as one Euler step moves every rate by
+< atol = 1e-5, i.e. ~1e-3 away from the true fixed point, so a solver that stops k
+sweeps earlier or later differs by k x 1e-5: matching the reference to better than
+1e-4 means stopping at the SAME sweep.
+* default kernel (register-resident W, FP32 FFMA on r - r_ref, float64 f and state):
+  rtol = atol = 1e-5 (BASELINE north_star asks 1e-4) and the sweep count of every
+  solve equal to the float64 oracle's (|difference| <= 1 tolerated, >= 95 % equal);
+* float64 kernel (`precise=True`, reference-ABI symbols): 1e-10, identical sweep counts;
+* shared-memory fallback kernel (sizes beyond 2N = 448; forced here with
+  SSN_FORCE_SMEM_KERNEL): rtol 1e-4 + atol 3e-4 as the reference's own cross-solver
+  tests (tc_gan/networks/tests/test_euler_ssn.py:36,86).
 """
+import os
 import numpy as np
 import pytest
 
@@ -16,7 +21,17 @@ from conftest import golden
 
 pytestmark = pytest.mark.gpu
 
-RTOL, ATOL = 1e-4, 3e-4
+RTOL, ATOL = 1e-5, 1e-5
+RTOL_SMEM, ATOL_SMEM = 1e-4, 3e-4
+
+
+def check_sweeps(its, it_ref):
+    its, it_ref = np.asarray(its, dtype=np.int64), np.asarray(it_ref, dtype=np.int64)
+    d = np.abs(its - it_ref)
+    # a marginally stable network (thousands of sweeps, |dr| shrinking by 0.1 % per sweep) may cross atol
+    # a few sweeps apart: allow 1 + 0.1 % of the reference count
+    assert (d <= 1 + it_ref // 1000).all(), (d.max(), it_ref[d.argmax()] if d.ndim == 1 else it_ref.ravel()[d.argmax()])
+    assert (d == 0).mean() >= 0.95, (d == 0).mean()
 
 
 @pytest.fixture(scope='module')
@@ -51,7 +66,7 @@ def test_golden_fixed_points(ssn, oracle, n_sites, io_type):
     np.testing.assert_allclose(Rp, g, rtol=0, atol=1e-10)
     _, _, it_ref = oracle.fixed_point_batch(W, exts, io_type=io_type, threads=4)
     np.testing.assert_array_equal(itsp, it_ref)
-    assert np.abs(its - it_ref).max() <= 40
+    check_sweeps(its, it_ref)
 
 
 @pytest.mark.parametrize('io_type', ['asym_linear', 'asym_power', 'asym_tanh'])
@@ -165,7 +180,9 @@ def test_ragged_shapes(ssn, oracle, n_sites, nz, nb):
     Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
     R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2)
     np.testing.assert_array_equal(err, st_o)
-    np.testing.assert_allclose(R, Ro, rtol=RTOL, atol=ATOL)
+    # (one seeded network here needs 9325 sweeps: a 3-sweep difference is 3e-5 in the rates)
+    np.testing.assert_allclose(R, Ro, rtol=RTOL, atol=ATOL * np.maximum(1, it_o[..., None] / 1000.0))
+    check_sweeps(its, it_o)
     Rp, errp, itsp = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, precise=True)
     np.testing.assert_array_equal(itsp, it_o)
     np.testing.assert_allclose(Rp, Ro, rtol=0, atol=1e-10)
@@ -186,6 +203,13 @@ def test_initial_state_and_max_iter(ssn, oracle):
                 assert code == 1
                 ref[z, b] = x
         np.testing.assert_allclose(R, ref, rtol=1e-5, atol=1e-5 if not precise else 1e-12)
+    # a non-zero initial state that does converge: same fixed point, same sweep count
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts)
+    x, code, it1 = oracle.fixed_point(W[1], exts[4], r0=r0)
+    R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, r0=r0)
+    assert (err == 0).all() and code == 0
+    np.testing.assert_allclose(R[1, 4], x, rtol=RTOL, atol=ATOL)
+    assert abs(int(its[1, 4]) - it1) <= 1
 
 
 def test_from_z_device_path_and_weight_kernel(ssn, oracle):
@@ -212,6 +236,40 @@ def test_from_z_device_path_and_weight_kernel(ssn, oracle):
     Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
     np.testing.assert_array_equal(st, st_o)
     np.testing.assert_allclose(R, Ro, rtol=RTOL, atol=ATOL)
+    check_sweeps(it, it_o)
+
+
+def test_tight_atol_on_the_fast_path(ssn, oracle):
+    """The reference-point iteration converges to atol far below FP32 resolution of the rates
+    (the reference's own tests use atol=1e-10, tc_gan/tests/test_ssn.py:66-74)."""
+    _, W, exts = seeded_problem(oracle, 51, 2, seed=4)
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, atol=1e-10, max_iter=100000)
+    R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, atol=1e-10, max_iter=100000)
+    assert (err == 0).all() and (st_o == 0).all()
+    np.testing.assert_allclose(R, Ro, rtol=1e-6, atol=1e-6)
+    assert np.abs(its - it_o).max() <= 2
+
+
+def test_shared_memory_fallback_kernel(ssn, oracle):
+    """The cluster/DSMEM kernel that keeps W in shared memory (used beyond 2N = 448)."""
+    os.environ['SSN_FORCE_SMEM_KERNEL'] = '1'
+    try:
+        for n_sites, nz in ((51, 3), (201, 2)):
+            _, W, exts = seeded_problem(oracle, n_sites, nz, seed=9)
+            Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+            R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2)
+            np.testing.assert_array_equal(err, st_o)
+            np.testing.assert_allclose(R, Ro, rtol=RTOL_SMEM, atol=ATOL_SMEM)
+            assert np.abs(its - it_o).max() <= 60
+    finally:
+        del os.environ['SSN_FORCE_SMEM_KERNEL']
+    # a size only the fallback covers
+    n_sites = 240
+    _, W, exts = seeded_problem(oracle, n_sites, 1, seed=10)
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+    R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2)
+    np.testing.assert_array_equal(err, st_o)
+    np.testing.assert_allclose(R, Ro, rtol=RTOL_SMEM, atol=ATOL_SMEM)
 
 
 def test_full_size_fixed_point_property(ssn, oracle):
@@ -251,4 +309,5 @@ def test_full_size_fixed_point_property(ssn, oracle):
     assert np.abs(step).max() < 5e-5
     Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
     np.testing.assert_allclose(Rs, Ro, rtol=RTOL, atol=ATOL)
+    check_sweeps(it[sample], it_o)
     assert np.isfinite(R.cpu().numpy()).all()

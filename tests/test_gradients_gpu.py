@@ -48,9 +48,9 @@ def test_ift_gradient_matches_oracle(ops, oracle, n_sites, nz, nb, io_type):
     gJ, gD, gS, mu_gpu, status, iters = ops.ift_gradient(tens(z), J, D, S, tens(exts), tens(R), tens(gR),
                                                          solver=solver, return_mu=True)
     assert (status.cpu().numpy() == 0).all()
-    np.testing.assert_allclose(mu_gpu.cpu().numpy(), mu, rtol=1e-3, atol=1e-3 * np.abs(mu).max())
-    for got, want in ((gJ, dJ), (gD, dD), (gS, dS)):
-        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-3, atol=1e-3 * np.abs(want).max())
+    np.testing.assert_allclose(mu_gpu.cpu().numpy(), mu, rtol=1e-3, atol=2e-4 * np.abs(mu).max())
+    for got, want in ((gJ, dJ), (gD, dD), (gS, dS)):      # north_star: generator gradients within rtol 1e-4
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
 
 
 def test_fixed_point_autograd_function(ops, oracle):
