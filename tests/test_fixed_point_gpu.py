@@ -30,7 +30,7 @@ def check_sweeps(its, it_ref):
     d = np.abs(its - it_ref)
     # a marginally stable network (thousands of sweeps, |dr| shrinking by 0.1 % per sweep) may cross atol
     # a few sweeps apart: allow 1 + 0.1 % of the reference count
-    assert (d <= 1 + it_ref // 1000).all(), (d.max(), it_ref[d.argmax()] if d.ndim == 1 else it_ref.ravel()[d.argmax()])
+    assert (d <= 1 + it_ref // 1000).all(), (int(d.max()), int(it_ref.ravel()[d.argmax()]))
     assert (d == 0).mean() >= 0.95, (d == 0).mean()
 
 
@@ -181,7 +181,8 @@ def test_ragged_shapes(ssn, oracle, n_sites, nz, nb):
     R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2)
     np.testing.assert_array_equal(err, st_o)
     # (one seeded network here needs 9325 sweeps: a 3-sweep difference is 3e-5 in the rates)
-    np.testing.assert_allclose(R, Ro, rtol=RTOL, atol=ATOL * np.maximum(1, it_o[..., None] / 1000.0))
+    tol = ATOL * np.maximum(1, it_o[..., None] / 1000.0) + RTOL * np.abs(Ro)
+    assert (np.abs(R - Ro) <= tol).all(), float((np.abs(R - Ro) / tol).max())
     check_sweeps(its, it_o)
     Rp, errp, itsp = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, precise=True)
     np.testing.assert_array_equal(itsp, it_o)
