@@ -151,6 +151,83 @@ def cpu_baseline(seconds_budget=20.0):
             'sample': '%d of %d networks x 8 stimuli, one pass (%.1f s)' % (nz, NZ, dt)}
 
 
+def run_gan_step(args):
+    """Secondary metric of BASELINE.json: GAN generator steps/s (configs[2] and configs[3]).
+    One step = forward + backward of the generator through the SSN with a fixed linear critic
+    (loss = <G, tuning curves> [+ penalties]), networks sharded over the ranks, ONE all-reduce
+    of the packed (dJ, dD, dS) gradient per step."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tc_gan_b200 import clib, ssnode, stimuli, torch_ops as ops
+    from tc_gan_b200 import dist as sdist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    P = ssnode.DEFAULT_PARAMS
+    jds = ssnode.new_JDS()
+    n_sites, dim = N_SITES, 2 * N_SITES
+    exts = torch.tensor(stimuli.input(NB_BANDWIDTHS, np.linspace(-.5, .5, n_sites), P['smoothness'], P['contrast']),
+                        dtype=torch.float32, device=dev)
+    total = 256 if args.workload == 'gan_fp' else 128
+    nz = len(sdist.shard_indices(total, rank, world))          # strong scaling: the step's networks are sharded
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    z = torch.rand((nz, dim, dim), generator=gen, device=dev)
+    G = torch.randn((nz, exts.shape[0], dim), generator=gen, device=dev)
+    J, D, S = (torch.tensor(jds[k], dtype=torch.float64, device=dev, requires_grad=True) for k in 'JDS')
+    launches0 = None
+
+    def step():
+        for p in (J, D, S):
+            p.grad = None
+        if args.workload == 'gan_fp':
+            R, status, _ = ops.ssn_fixed_point(z, J, D, S, exts)
+            loss = (R * G).sum()
+        else:
+            avg, dyn, rate = ops.euler_ssn(z, J, D, S, exts, seqlen=1200, skip_steps=1000)
+            loss = (avg * G).sum() + 0.1 * dyn + 0.01 * rate
+        loss.backward()
+        return sdist.allreduce_generator_grads(J.grad, D.grad, S.grad)
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = clib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'GAN generator steps/sec (%s)' % ('fixed-point, implicit gradient' if args.workload == 'gan_fp'
+                                                       else 'BPTT, seqlen 1200'),
+            'value': args.steps / (ms.item() * 1e-3), 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms.item() / args.steps, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 contraction / f64 state', 'data': 'synthetic',
+            'config': {'workload': ('configs[3]: fixed-point GAN generator step, 256 networks x 8 stimuli, 2N=402'
+                                    if args.workload == 'gan_fp' else
+                                    'configs[2]: bptt_cwgan generator step, 128 networks x 8 stimuli, 2N=402, seqlen 1200'),
+                       'critic': 'fixed linear functional (no critic network on this path)',
+                       'collective': 'one all-reduce of the packed 12-double (dJ, dD, dS) per step'},
+            'gpu_launches': clib.kernel_launches() - launches0}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -159,10 +236,15 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--networks', type=int, default=NZ, help='networks per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='solve', choices=['solve', 'gan_fp', 'gan_bptt'],
+                    help='solve: configs[1] (default, the BASELINE metric); gan_fp: configs[3] fixed-point '
+                         'generator step (256 networks/step sharded over the ranks); gan_bptt: configs[2] BPTT step')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload != 'solve':
+        return run_gan_step(args)
 
     import numpy as np
     import torch

@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                                          *reinterpret_cast<const unsigned *>(xb + lane * RW_BLK_BYTES) |
                                          *reinterpret_cast<const unsigned *>(xb + (lane + 32) * RW_BLK_BYTES));
                 }
+                if (a.dbg & 1) F = 0x00ff00ffu;          // timing experiment: no exchange, nobody converges or refreshes
                 if (it > 1) {
                     const unsigned moving_all = F & 0xffu, above_all = (F >> 8) & 0xffu;
                     const unsigned conv_now = ~moving_all & ~done & 0xffu;       // ssnode.c:84-96 first ...
