@@ -57,6 +57,7 @@ struct RwArgs {
     IoConst<float> iof;
     double eps_E, eps_I, atol, r_hard, t_first;        // t_first: first refresh threshold on |dr|
     int max_iter, check_hard, tab_nodes;
+    float tab_end;                                     // v at the last table node
     int dbg;                                           // development switches (SSN_DBG), 0 in production
     long long *dbg_out;                                // phase cycle counters when dbg & 4
 };
@@ -141,24 +142,30 @@ __device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long lon
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(xx));
 }
 
-// f(v) in float64: cubic expansion around the nearest table node for v in [1, table end],
-// accurate float for v < 1 (|f| < k: absolute error ~1e-9 k), closed form above the table.
+// f(v) in float64.  Common case (1 <= v within the table, power-law branch): cubic expansion around the
+// nearest node -- index from an FP32 estimate, offset and Horner in FP64, no branches.  v < 1: accurate
+// enough in FP32 (|f| < k, absolute error ~1e-8 k).  Above the soft bound / beyond the table: closed form
+// behind a (rare, warp-divergent) branch.
 __device__ __forceinline__ double io_eval_table(const RwArgs &a, const double *tab, double v) {
-    if (!(v > 0.0)) return v != v ? v : 0.0;
-    if (v < TAB_V_MIN) return (double)(a.iof.k * exp2f(a.iof.n * __log2f((float)v)));   // |f| < k, abs. error ~1e-8 k
-    const double x = (v - TAB_V_MIN) * TAB_PER_UNIT;
+    const float vf = (float)v;
+    int i = __float2int_rn((vf - (float)TAB_V_MIN) * (float)TAB_PER_UNIT);
+    i = max(0, min(i, a.tab_nodes - 1));
+    const double s = fma(v, (double)TAB_PER_UNIT, -TAB_V_MIN * TAB_PER_UNIT) - (double)i;
+    const double2 c01 = *reinterpret_cast<const double2 *>(tab + 4 * i);
+    const double2 c23 = *reinterpret_cast<const double2 *>(tab + 4 * i + 2);
+    double f = fma(s, fma(s, fma(s, c23.y, c23.x), c01.y), c01.x);
+    const float flow = a.iof.k * exp2f(a.iof.n * __log2f(fmaxf(vf, 1e-30f)));
+    f = vf < (float)TAB_V_MIN ? (double)flow : f;
+    f = v > 0.0 ? f : (v != v ? v : 0.0);
     const bool upper = a.io.io_type != SSN_IO_POWER && v > a.io.v0;
-    if (!upper && x < (double)(a.tab_nodes - 1)) {
-        const int i = __double2int_rn(x);
-        const double s = x - (double)i;
-        const double *c = tab + 4 * i;
-        return fma(s, fma(s, fma(s, c[3], c[2]), c[1]), c[0]);
+    if (upper || vf >= a.tab_end) {                       // rare: saturating / diverging neurons
+        if (upper)
+            f = a.io.io_type == SSN_IO_LINEAR ? fma(a.io.lin_slope, v - a.io.v0, a.io.r_soft)
+                                              : a.io.r_soft + a.io.span * tanh(a.io.tanh_scale * (v - a.io.v0));
+        else
+            f = a.io.k * pow(v, a.io.n);
     }
-    if (upper) {
-        if (a.io.io_type == SSN_IO_LINEAR) return fma(a.io.lin_slope, v - a.io.v0, a.io.r_soft);
-        return a.io.r_soft + a.io.span * tanh(a.io.tanh_scale * (v - a.io.v0));
-    }
-    return a.io.k * pow(v, a.io.n);                     // beyond the table (diverging power-law network)
+    return f;
 }
 
 template <int NC, int NW>
@@ -257,25 +264,36 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
         unsigned long long wp[3][NC];                              // rows (0,1), (2,3), (4,5) as packed pairs
         float ws[NC];                                              // row 6
         {
-            const float *src = a.w + (size_t)net * dim * dim;
+            // all 7 x NC loads are issued before any is consumed (one round trip to L2/HBM, not 98)
+            const float *src = a.w + (size_t)net * dim * dim + (size_t)(row_base + row0) * dim + lane;
+            float zv[RW_TI][NC];
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int j = c * 32 + lane;
-                float wv[RW_TI];
+            for (int t = 0; t < RW_TI; ++t)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    zv[t][c] = (row0 + t < rows_here && c * 32 + lane < dim) ? __ldg(src + (size_t)t * dim + c * 32) : 0.f;
+            if (a.w_kind == SSN_W_FROM_Z) {
 #pragma unroll
                 for (int t = 0; t < RW_TI; ++t) {
                     const int i = row_base + row0 + t;
-                    float v = 0.f;
-                    if (row0 + t < rows_here && j < dim) {
-                        v = __ldg(src + (size_t)i * dim + j);
-                        if (a.w_kind == SSN_W_FROM_Z) v = weight_from_z(a.wc, gtab, N, i, j, v);
+                    const int ah = i >= N, ii = i - ah * N;
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const int j = c * 32 + lane;
+                        const int bh = j >= N, ab = ah * 2 + bh;
+                        int d = ii - (j - bh * N);
+                        d = d < 0 ? -d : d;
+                        const bool ok = row0 + t < rows_here && j < dim;
+                        zv[t][c] = ok ? gtab[ab * N + min(d, N - 1)] * fmaf(a.wc.sD[ab], zv[t][c], a.wc.sJ[ab]) : 0.f;
                     }
-                    wv[t] = v;
                 }
-                wp[0][c] = pack2(wv[0], wv[1]);
-                wp[1][c] = pack2(wv[2], wv[3]);
-                wp[2][c] = pack2(wv[4], wv[5]);
-                ws[c] = wv[6];
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                wp[0][c] = pack2(zv[0][c], zv[1][c]);
+                wp[1][c] = pack2(zv[2][c], zv[3][c]);
+                wp[2][c] = pack2(zv[4][c], zv[5][c]);
+                ws[c] = zv[6][c];
             }
         }
 
@@ -523,13 +541,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                         double r_cur = r_old;
                         const double tl = misc->tlevel[(levels >> (4 * i)) & 7u];
                         if (!((done >> st) & 1u)) {
-                            const double r_new = r_old + (fv - r_old) * eps_own;
-                            const double step = fabs(r_new - r_old);
+                            const double d = (fv - r_old) * eps_own;               // r_new - r_old
+                            const double step = fabs(d);
+                            r_cur = r_old + d;
                             if (step >= a.atol) word |= 1u << st;
-                            if (r_new >= a.r_hard) word |= 1u << (8 + st);
+                            if (r_cur >= a.r_hard) word |= 1u << (8 + st);
                             if (step >= tl) word |= 1u << (16 + st);
-                            sR[i * RW_THREADS] = r_new;
-                            r_cur = r_new;
+                            sR[i * RW_THREADS] = r_cur;
                         }
                         if (!(tl > 0.0)) word |= 1u << (16 + st);              // ladder exhausted: never request again
                         xn[i] = (float)(r_cur - sRref[i * RW_THREADS]);
@@ -690,6 +708,7 @@ int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, i
     a.atol = sv.atol; a.r_hard = sv.rate_hard_bound;
     a.max_iter = sv.max_iter; a.check_hard = sv.io_type != SSN_IO_TANH;
     a.tab_nodes = plan.tab_nodes;
+    a.tab_end = (float)(TAB_V_MIN + (double)(plan.tab_nodes - 1) / TAB_PER_UNIT - 0.5 / TAB_PER_UNIT);
     a.dbg = getenv("SSN_DBG") ? atoi(getenv("SSN_DBG")) : 0;
     // refresh ladder: thresholds atol * 64^j, starting at the largest one below 0.1
     double t = sv.atol > 0 ? sv.atol : 1e-300;
