@@ -168,6 +168,22 @@ __device__ __forceinline__ double io_eval_table(const RwArgs &a, const double *t
     return f;
 }
 
+// Common path of io_eval_table without the rare branch; `rare` reports whether the closed form is needed.
+__device__ __forceinline__ double io_eval_common(const RwArgs &a, const double *tab, double v, bool &rare) {
+    const float vf = (float)v;
+    int i = __float2int_rn((vf - (float)TAB_V_MIN) * (float)TAB_PER_UNIT);
+    i = max(0, min(i, a.tab_nodes - 1));
+    const double s = fma(v, (double)TAB_PER_UNIT, -TAB_V_MIN * TAB_PER_UNIT) - (double)i;
+    const double2 c01 = *reinterpret_cast<const double2 *>(tab + 4 * i);
+    const double2 c23 = *reinterpret_cast<const double2 *>(tab + 4 * i + 2);
+    double f = fma(s, fma(s, fma(s, c23.y, c23.x), c01.y), c01.x);
+    const float flow = a.iof.k * exp2f(a.iof.n * __log2f(fmaxf(vf, 1e-30f)));
+    f = vf < (float)TAB_V_MIN ? (double)flow : f;
+    f = v > 0.0 ? f : (v != v ? v : 0.0);
+    rare = (a.io.io_type != SSN_IO_POWER && v > a.io.v0) || vf >= a.tab_end;
+    return f;
+}
+
 template <int NC, int NW>
 __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(const RwArgs a) {
     constexpr int RW_WARPS = NW, RW_THREADS = 32 * NW;
@@ -532,25 +548,34 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                 unsigned word = 0u;
                 if (owner) {
                     float xn[2];
+                    // both outputs: loads and the branch-free common path first (two independent FP64 chains)
+                    double vv[2], fv[2], r_old[2], r_ref2[2], tl[2];
+                    bool rare[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        vv[i] = sVref[i * RW_THREADS] + (double)dv[i];
+                        r_old[i] = sR[i * RW_THREADS];
+                        r_ref2[i] = sRref[i * RW_THREADS];
+                        tl[i] = misc->tlevel[(levels >> (4 * i)) & 7u];
+                        fv[i] = io_eval_common(a, tab, vv[i], rare[i]);
+                    }
+                    if (rare[0] | rare[1]) {                                   // saturating / diverging neurons only
+                        if (rare[0]) fv[0] = io_eval_table(a, tab, vv[0]);
+                        if (rare[1]) fv[1] = io_eval_table(a, tab, vv[1]);
+                    }
+                    if (a.dbg & 2) { fv[0] = vv[0]; fv[1] = vv[1]; }
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int st = my_st0 + i;
-                        const double v = sVref[i * RW_THREADS] + (double)dv[i];
-                        const double fv = (a.dbg & 2) ? v : io_eval_table(a, tab, v);
-                        const double r_old = sR[i * RW_THREADS];
-                        double r_cur = r_old;
-                        const double tl = misc->tlevel[(levels >> (4 * i)) & 7u];
-                        if (!((done >> st) & 1u)) {
-                            const double d = (fv - r_old) * eps_own;               // r_new - r_old
-                            const double step = fabs(d);
-                            r_cur = r_old + d;
-                            if (step >= a.atol) word |= 1u << st;
-                            if (r_cur >= a.r_hard) word |= 1u << (8 + st);
-                            if (step >= tl) word |= 1u << (16 + st);
-                            sR[i * RW_THREADS] = r_cur;
-                        }
-                        if (!(tl > 0.0)) word |= 1u << (16 + st);              // ladder exhausted: never request again
-                        xn[i] = (float)(r_cur - sRref[i * RW_THREADS]);
+                        const bool live = !((done >> st) & 1u);
+                        const double d = live ? (fv[i] - r_old[i]) * eps_own : 0.0;   // r_new - r_old
+                        const double step = fabs(d);
+                        const double r_cur = r_old[i] + d;
+                        if (live && step >= a.atol) word |= 1u << st;
+                        if (live && r_cur >= a.r_hard) word |= 1u << (8 + st);
+                        if ((live && step >= tl[i]) || !(tl[i] > 0.0)) word |= 1u << (16 + st);   // exhausted ladder never asks
+                        if (live) sR[i * RW_THREADS] = r_cur;
+                        xn[i] = (float)(r_cur - r_ref2[i]);
                     }
                     *reinterpret_cast<float2 *>(smem + L.x_off + nbuf * RW_BUF_BYTES + xoff) = make_float2(xn[0], xn[1]);
                 }
