@@ -99,7 +99,7 @@ def run_reference(args):
     import ssn_oracle as so
     cores = int(os.environ.get('OMP_NUM_THREADS', 0)) or (os.cpu_count() or 1)
     kind = 'reference' if so.ref_lib() is not None else 'port'
-    nz = max(8, min(64, 2 * cores))            # bounded sample of the 1024-network step
+    nz = max(8, min(NZ, 32 * cores))            # bounded sample of the 1024-network step (~5 s of CPU work per step)
     jds = so.new_JDS()
     exts = so.stimulus_input(so.DEFAULT_BANDWIDTHS, N_SITES)
     rs = np.random.RandomState(0)
@@ -136,7 +136,7 @@ def cpu_baseline(seconds_budget=20.0):
     import ssn_oracle as so
     cores = int(os.environ.get('OMP_NUM_THREADS', 0)) or (os.cpu_count() or 1)
     kind = 'reference' if so.ref_lib() is not None else 'port'
-    nz = max(8, min(64, 2 * cores))
+    nz = max(8, min(NZ, 64 * cores))             # ~10 s of CPU work on all host cores
     jds = so.new_JDS()
     exts = so.stimulus_input(so.DEFAULT_BANDWIDTHS, N_SITES)
     z = np.random.RandomState(0).rand(nz, 2 * N_SITES, 2 * N_SITES).astype(np.float32).astype(np.float64)

@@ -47,7 +47,7 @@ static int next_counter(int **out) {
 // ---- per-thread host staging ------------------------------------------------------
 struct HostCtx {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
     std::vector<void *> slot;
     std::vector<size_t> cap;
     int ensure_device() {
@@ -58,6 +58,11 @@ struct HostCtx {
             device = dev;
             SSN_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         }
+        return 0;
+    }
+    int second_stream(cudaStream_t *out) {
+        if (!stream2) SSN_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+        *out = stream2;
         return 0;
     }
     int get(int i, size_t bytes, void **out) {
@@ -75,7 +80,8 @@ struct HostCtx {
         for (void *p : slot) if (p) cudaFree(p);
         slot.clear(); cap.clear();
         if (stream) cudaStreamDestroy(stream);
-        stream = nullptr;
+        if (stream2) cudaStreamDestroy(stream2);
+        stream = nullptr; stream2 = nullptr;
     }
     ~HostCtx() { release(); }
 };
@@ -266,40 +272,52 @@ int ssn_fixed_point_batch(const ssn_solver *solver, int nz, int nb, int n_sites,
         return check_cuda(cudaStreamSynchronize(st), "precise device path");
     }
 
-    // host arrays: stage through this thread's buffers in slabs of networks
+    // host arrays: slabs of networks through two staging slots on two streams, so the H2D copy of one
+    // slab and the D2H copy of the previous one overlap the solve of the current one (pinned host
+    // memory makes the copies truly asynchronous; pageable memory still works, just without overlap)
     if ((rc = tl_ctx.ensure_device())) return rc;
-    cudaStream_t st = tl_ctx.stream;
-    const int slab = std::min(nz, 2048);
+    cudaStream_t streams[2] = {tl_ctx.stream, nullptr};
+    if ((rc = tl_ctx.second_stream(&streams[1]))) return rc;
+    const int slab = std::min(nz, precise ? 256 : 128);
     const size_t n_ext = (size_t)(ext_per_network ? slab : 1) * nb * dim;
-    GET(8, float, (size_t)slab * dim * dim, dw);
-    GET(9, float, n_ext, de);
-    GET(10, float, (size_t)slab * nb * dim, dr0);
-    GET(11, float, (size_t)slab * nb * dim, dr);
-    GET(12, int, (size_t)slab * nb * 2, ds);
-    if (!ext_per_network) SSN_CUDA(cudaMemcpyAsync(de, ext, n_ext * sizeof(float), cudaMemcpyHostToDevice, st));
-    for (int z0 = 0; z0 < nz; z0 += slab) {
+    float *dw[2], *de[2], *dr0[2], *dr[2];
+    int *ds[2];
+    for (int q = 0; q < 2; ++q) {
+        void *p;
+        if ((rc = tl_ctx.get(16 + 5 * q + 0, (size_t)slab * dim * dim * sizeof(float), &p))) return rc; dw[q] = (float *)p;
+        if ((rc = tl_ctx.get(16 + 5 * q + 1, n_ext * sizeof(float), &p))) return rc; de[q] = (float *)p;
+        if ((rc = tl_ctx.get(16 + 5 * q + 2, (size_t)slab * nb * dim * sizeof(float), &p))) return rc; dr0[q] = (float *)p;
+        if ((rc = tl_ctx.get(16 + 5 * q + 3, (size_t)slab * nb * dim * sizeof(float), &p))) return rc; dr[q] = (float *)p;
+        if ((rc = tl_ctx.get(16 + 5 * q + 4, (size_t)slab * nb * 2 * sizeof(int), &p))) return rc; ds[q] = (int *)p;
+        if (!ext_per_network)
+            SSN_CUDA(cudaMemcpyAsync(de[q], ext, n_ext * sizeof(float), cudaMemcpyHostToDevice, streams[q]));
+    }
+    int q = 0;
+    for (int z0 = 0; z0 < nz; z0 += slab, q ^= 1) {
         const int m = std::min(slab, nz - z0);
-        SSN_CUDA(cudaMemcpyAsync(dw, w + (size_t)z0 * dim * dim, (size_t)m * dim * dim * sizeof(float),
+        cudaStream_t st = streams[q];
+        SSN_CUDA(cudaMemcpyAsync(dw[q], w + (size_t)z0 * dim * dim, (size_t)m * dim * dim * sizeof(float),
                                  cudaMemcpyHostToDevice, st));
         if (ext_per_network)
-            SSN_CUDA(cudaMemcpyAsync(de, ext + (size_t)z0 * nb * dim, (size_t)m * nb * dim * sizeof(float),
+            SSN_CUDA(cudaMemcpyAsync(de[q], ext + (size_t)z0 * nb * dim, (size_t)m * nb * dim * sizeof(float),
                                      cudaMemcpyHostToDevice, st));
         if (r_init)
-            SSN_CUDA(cudaMemcpyAsync(dr0, r_init + (size_t)z0 * nb * dim, (size_t)m * nb * dim * sizeof(float),
+            SSN_CUDA(cudaMemcpyAsync(dr0[q], r_init + (size_t)z0 * nb * dim, (size_t)m * nb * dim * sizeof(float),
                                      cudaMemcpyHostToDevice, st));
-        rc = ssn_fixed_point_batch(solver, m, nb, n_sites, w_kind, dw, jds, de, ext_per_network,
-                                   r_init ? dr0 : nullptr, dr, ds, ds + (size_t)slab * nb, precise,
+        rc = ssn_fixed_point_batch(solver, m, nb, n_sites, w_kind, dw[q], jds, de[q], ext_per_network,
+                                   r_init ? dr0[q] : nullptr, dr[q], ds[q], ds[q] + (size_t)slab * nb, precise,
                                    SSN_MEM_DEVICE, st);
         if (rc) return rc;
-        SSN_CUDA(cudaMemcpyAsync(R + (size_t)z0 * nb * dim, dr, (size_t)m * nb * dim * sizeof(float),
+        SSN_CUDA(cudaMemcpyAsync(R + (size_t)z0 * nb * dim, dr[q], (size_t)m * nb * dim * sizeof(float),
                                  cudaMemcpyDeviceToHost, st));
-        SSN_CUDA(cudaMemcpyAsync(status + (size_t)z0 * nb, ds, (size_t)m * nb * sizeof(int),
+        SSN_CUDA(cudaMemcpyAsync(status + (size_t)z0 * nb, ds[q], (size_t)m * nb * sizeof(int),
                                  cudaMemcpyDeviceToHost, st));
         if (iters)
-            SSN_CUDA(cudaMemcpyAsync(iters + (size_t)z0 * nb, ds + (size_t)slab * nb, (size_t)m * nb * sizeof(int),
+            SSN_CUDA(cudaMemcpyAsync(iters + (size_t)z0 * nb, ds[q] + (size_t)slab * nb, (size_t)m * nb * sizeof(int),
                                      cudaMemcpyDeviceToHost, st));
-        SSN_CUDA(cudaStreamSynchronize(st));
     }
+    SSN_CUDA(cudaStreamSynchronize(streams[0]));
+    SSN_CUDA(cudaStreamSynchronize(streams[1]));
     return 0;
 }
 
