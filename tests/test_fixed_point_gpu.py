@@ -312,3 +312,27 @@ def test_full_size_fixed_point_property(ssn, oracle):
     np.testing.assert_allclose(Rs, Ro, rtol=RTOL, atol=ATOL)
     check_sweeps(it[sample], it_o)
     assert np.isfinite(R.cpu().numpy()).all()
+
+
+def test_sample_tuning_curves_dataset_path(ssn, oracle):
+    """truth-dataset generation through the solver, as networks/dataset.py:28-71 calls
+    ssnode.sample_tuning_curves (asym_power + rate_stop_at: rejected networks are re-drawn)."""
+    kw = dict(NZ=5, seed=1, N=51, io_type='asym_power', rate_stop_at=200, max_iter=3000,
+              sample_sites=[12, 25, 38])
+    tunings, (zs, rates, info) = ssn.sample_tuning_curves(track_offset_identity=True, **kw)
+    assert tunings.shape == (3 * 8, 5) and rates.shape == (5, 8, 102) and zs.shape == (5, 102, 102)
+    np.testing.assert_array_equal(tunings.T.reshape(5, 8, 3), rates[:, :, [12, 25, 38]])
+    # every kept network is a genuine fixed point of the reference dynamics and was drawn in order
+    rs = np.random.RandomState(1)
+    P = ssn.DEFAULT_PARAMS
+    exts = oracle.stimulus_input(P['bandwidths'], 51)
+    kept = 0
+    for _ in range(5 + info.rejections):
+        z = rs.rand(1, 102, 102)[0]
+        W = oracle.generate_weight(51, P['J'], P['D'], P['S'], z)
+        R, st, _ = oracle.fixed_point_batch(W[None], exts, io_type='asym_power', rate_stop_at=200, max_iter=3000)
+        if (st == 0).all():
+            np.testing.assert_array_equal(z, zs[kept])
+            np.testing.assert_allclose(rates[kept], R[0], rtol=RTOL, atol=ATOL)
+            kept += 1
+    assert kept == 5 and info.unused == 0
