@@ -466,32 +466,39 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                 const int nbuf = buf ^ 1;
                 long long c2 = clock64(); tc[1] += c2 - c1;
                 if (tid == 0) mbar_arrive_expect_tx(full_local[nbuf], tx_bytes);
+                // Half-panel-major: the four stimuli of a half share one LDS.128 per column; a half whose stimuli
+                // have all finished is skipped (uniform over the cluster).  Sixteen independent FMA chains per half.
                 float acc[RW_TI][TB];
                 {
-                    unsigned long long ap[3][TB];
-                    float as[TB];
-#pragma unroll
-                    for (int b = 0; b < TB; ++b) { ap[0][b] = 0ull; ap[1][b] = 0ull; ap[2][b] = 0ull; as[b] = 0.f; }
                     const float4 *Xq = reinterpret_cast<const float4 *>(smem + L.x_off + buf * RW_BUF_BYTES);
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const unsigned slot = (c & 1) ? (colslot[c / 2] >> 16) : (colslot[c / 2] & 0xffffu);
-                        const float4 xa = Xq[slot], xb = Xq[slot + RW_TI];
-                        const float xv[TB] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                    for (int h = 0; h < 2; ++h) {
+                        unsigned long long ap[3][4];
+                        float as[4];
 #pragma unroll
-                        for (int b = 0; b < TB; ++b) {
-                            ffma2(ap[0][b], wp[0][c], xv[b]);
-                            ffma2(ap[1][b], wp[1][c], xv[b]);
-                            ffma2(ap[2][b], wp[2][c], xv[b]);
-                            as[b] = fmaf(ws[c], xv[b], as[b]);
+                        for (int b = 0; b < 4; ++b) { ap[0][b] = 0ull; ap[1][b] = 0ull; ap[2][b] = 0ull; as[b] = 0.f; }
+                        if (((done >> (4 * h)) & 0xfu) != 0xfu) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                const unsigned slot = (c & 1) ? (colslot[c / 2] >> 16) : (colslot[c / 2] & 0xffffu);
+                                const float4 x4 = Xq[slot + RW_TI * h];
+                                const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) {
+                                    ffma2(ap[0][b], wp[0][c], xv[b]);
+                                    ffma2(ap[1][b], wp[1][c], xv[b]);
+                                    ffma2(ap[2][b], wp[2][c], xv[b]);
+                                    as[b] = fmaf(ws[c], xv[b], as[b]);
+                                }
+                            }
                         }
-                    }
 #pragma unroll
-                    for (int b = 0; b < TB; ++b) {
-                        unpack2(ap[0][b], acc[0][b], acc[1][b]);
-                        unpack2(ap[1][b], acc[2][b], acc[3][b]);
-                        unpack2(ap[2][b], acc[4][b], acc[5][b]);
-                        acc[6][b] = as[b];
+                        for (int b = 0; b < 4; ++b) {
+                            unpack2(ap[0][b], acc[0][4 * h + b], acc[1][4 * h + b]);
+                            unpack2(ap[1][b], acc[2][4 * h + b], acc[3][4 * h + b]);
+                            unpack2(ap[2][b], acc[4][4 * h + b], acc[5][4 * h + b]);
+                            acc[6][4 * h + b] = as[b];
+                        }
                     }
                 }
                 long long c3 = clock64(); tc[2] += c3 - c2;
