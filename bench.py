@@ -228,6 +228,56 @@ def run_gan_step(args):
         dist.destroy_process_group()
 
 
+def run_wgan(args):
+    """Full WGAN-GP training steps (5 critic updates + 1 generator update per step) with the torch MLP
+    critic of tc_gan_b200.gan around the CUDA generator; synthetic 'true' tuning curves."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tc_gan_b200 import clib, gan
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    mode = 'fixed_point' if args.workload == 'wgan_fp' else 'bptt'
+    num_models = 256 if mode == 'fixed_point' else 128
+    data = np.abs(np.random.RandomState(0).randn(1024, 8)).astype(np.float32) * 10
+    g = gan.SSNWassersteinGAN(data, num_sites=N_SITES, mode=mode, num_models=num_models, sample_sites=(0,),
+                              critic_iters_init=5, critic_iters=5, device=dev)
+    steps = g.learning()
+
+    def gen_step():
+        for info in steps:
+            if not info['is_discriminator']:
+                return info
+
+    for _ in range(max(1, args.warmup // 3)):
+        gen_step()
+    torch.cuda.synchronize()
+    launches0 = clib.kernel_launches()
+    t0 = time.time()
+    for _ in range(args.steps):
+        info = gen_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.time() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'WGAN-GP training steps/sec (5 critic + 1 generator update, %s generator)' % mode,
+            'value': args.steps / dt.item(), 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt.item() / args.steps * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 contraction / f64 state', 'data': 'synthetic',
+            'config': {'workload': '%d networks x 8 stimuli per update, 2N=402, critic MLP 128-128' % num_models,
+                       'last_gen_loss': info['gen_loss'], 'rejections': g.rejections},
+            'gpu_launches': clib.kernel_launches() - launches0}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -236,13 +286,15 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--networks', type=int, default=NZ, help='networks per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--workload', default='solve', choices=['solve', 'gan_fp', 'gan_bptt'],
+    ap.add_argument('--workload', default='solve', choices=['solve', 'gan_fp', 'gan_bptt', 'wgan_fp', 'wgan_bptt'],
                     help='solve: configs[1] (default, the BASELINE metric); gan_fp: configs[3] fixed-point '
                          'generator step (256 networks/step sharded over the ranks); gan_bptt: configs[2] BPTT step')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload in ('wgan_fp', 'wgan_bptt'):
+        return run_wgan(args)
     if args.workload != 'solve':
         return run_gan_step(args)
 

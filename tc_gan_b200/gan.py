@@ -1,0 +1,186 @@
+"""
+WGAN-GP learners over the CUDA SSN generator -- SURVEY.md section 8f rank 1 (the first
+caller of the hot path), kept deliberately small: the critic is a few-hundred-unit MLP
+(torch.nn), all of the simulation work stays in libssnode.so.
+
+What it mirrors in the reference (tc_gan/networks/wgan.py unless noted):
+  * critic loss  mean D(fake) - mean D(real) + lambda * mean (||grad_x D(x_hat)||_2 - 1)^2
+    with x_hat = eps * real + (1 - eps) * fake                      :194-215, :380-395
+  * generator loss  -mean D(G(z)) + dynamics_cost * dynamics_penalty + rate_cost * rate_penalty
+    and clipping of J, D, S to [min, max] after each update           :218-254
+  * updates 'adam-wgan' = Adam(beta1=0.5, beta2=0.9)                  :112-118
+  * schedule: critic_iters_init critic steps before the first generator step, then
+    critic_iters per generator step                                   :430-444
+  * defaults (seqlen 1200, skip_steps 1000, dt 0.1, tau (10, 1), rate_cost 0.01,
+    rate_penalty_threshold 200)                                       :39-63
+  * the fixed-point ("legacy") GAN of tc_gan/run/gan.py:617-672, 830-941: generator = fixed
+    points of sampled networks, rejected networks re-drawn, implicit gradient.
+Tuning curves fed to the critic are rates probed at `sample_sites`
+(gradient_expressions/utils.py:74-149, track_offset_identity=True layout).
+
+Multi-GPU: networks of a generator batch are sharded over the ranks; the only collective
+on the generator path is one all-reduce of the packed (dJ, dD, dS); critic gradients are
+all-reduced as usual data-parallel training does.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import dist as sdist
+from . import ssnode, stimuli, torch_ops
+from .gradient_expressions.utils import sample_sites_from_stim_space, subsample_neurons
+
+
+class Critic(nn.Module):
+    """MLP critic, tc_gan/networks/simple_discriminator.py:6-75 (rectifier units, optional
+    layer normalisation, linear output for the WGAN loss)."""
+
+    def __init__(self, n_in, layers=(128, 128), layer_norm=False):
+        super().__init__()
+        mods, width = [], n_in
+        for units in layers:
+            mods.append(nn.Linear(width, units))
+            if layer_norm:
+                mods.append(nn.LayerNorm(units))
+            mods.append(nn.ReLU())
+            width = units
+        mods.append(nn.Linear(width, 1))
+        self.net = nn.Sequential(*mods)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def critic_loss(critic, fake, real, lipschitz_cost=10.0, generator=None):
+    """WGAN-GP critic loss and the accuracy D(fake) - D(real) (wgan.py:194-215, :90)."""
+    eps = torch.rand((real.shape[0], 1), device=real.device, dtype=real.dtype, generator=generator)
+    n = min(len(fake), len(real))
+    x_hat = (eps[:n] * real[:n] + (1 - eps[:n]) * fake[:n]).requires_grad_(True)
+    grad, = torch.autograd.grad(critic(x_hat).sum(), x_hat, create_graph=True)
+    penalty = ((grad.norm(2, dim=1) - 1) ** 2).mean()
+    d_fake, d_real = critic(fake).mean(), critic(real).mean()
+    return d_fake - d_real + lipschitz_cost * penalty, (d_fake - d_real).detach()
+
+
+class SSNWassersteinGAN(object):
+    """
+    One object for both generator flavours:
+      mode='fixed_point' -- tuning curves from converged fixed points, implicit gradient;
+      mode='bptt'        -- tuning curves from the time-averaged unrolled Euler dynamics, BPTT.
+    `data` is [n_data, nb * len(sample_sites)] true tuning curves.
+    """
+
+    def __init__(self, data, num_sites=ssnode.DEFAULT_PARAMS['N'], mode='fixed_point',
+                 J=None, D=None, S=None,
+                 bandwidths=ssnode.DEFAULT_PARAMS['bandwidths'], contrasts=(20.,),
+                 smoothness=ssnode.DEFAULT_PARAMS['smoothness'], sample_sites=(0,),
+                 num_models=128, io_type='asym_tanh', k=0.01, n=2.2,
+                 seqlen=1200, skip_steps=1000, dt=0.1, tau_E=10., tau_I=1.,
+                 dynamics_cost=0.0, rate_cost=0.01, rate_penalty_threshold=200.0,
+                 critic_layers=(128, 128), layer_norm=False,
+                 critic_iters_init=50, critic_iters=5, lipschitz_cost=10.0,
+                 gen_learning_rate=0.001, disc_learning_rate=0.001,
+                 param_min=1e-3, param_max=10.0, seed=0, device='cuda', solver_kwargs=None):
+        if mode not in ('fixed_point', 'bptt'):
+            raise ValueError('Unknown mode: {}'.format(mode))
+        self.mode, self.num_sites, self.num_models = mode, int(num_sites), int(num_models)
+        self.device = torch.device(device)
+        jds = ssnode.new_JDS()
+        mk = lambda a, key: torch.tensor(np.asarray(jds[key] if a is None else a), dtype=torch.float64,
+                                         device=self.device, requires_grad=True)
+        self.J, self.D, self.S = mk(J, 'J'), mk(D, 'D'), mk(S, 'S')
+        x = np.linspace(-0.5, 0.5, self.num_sites)
+        self.exts = torch.tensor(stimuli.input(bandwidths, x, smoothness, list(contrasts)),
+                                 dtype=torch.float32, device=self.device)
+        # probe locations are given in stimulus space [-1, 1] (wgan.py:30, probes_from_stim_space)
+        self.sample_sites = sample_sites_from_stim_space(list(sample_sites), self.num_sites)
+        self.data = torch.as_tensor(data, dtype=torch.float32, device=self.device)
+        n_in = self.exts.shape[0] * len(self.sample_sites)
+        assert self.data.shape[1] == n_in, (self.data.shape, n_in)
+        torch.manual_seed(seed)
+        self.critic = Critic(n_in, critic_layers, layer_norm).to(self.device)
+        self.opt_gen = torch.optim.Adam([self.J, self.D, self.S], lr=gen_learning_rate, betas=(0.5, 0.9))
+        self.opt_disc = torch.optim.Adam(self.critic.parameters(), lr=disc_learning_rate, betas=(0.5, 0.9))
+        self.rng = torch.Generator(device=self.device)
+        rank, world = sdist.world()
+        self.rng.manual_seed(seed * 1000 + rank)
+        self.local_models = len(sdist.shard_indices(self.num_models, rank, world))
+        self.io = dict(io_type=io_type, k=k, n=n)
+        self.euler = dict(seqlen=seqlen, skip_steps=skip_steps, dt=dt, tau_E=tau_E, tau_I=tau_I)
+        self.costs = dict(dynamics_cost=dynamics_cost, rate_cost=rate_cost,
+                          rate_penalty_threshold=rate_penalty_threshold)
+        self.critic_iters_init, self.critic_iters = critic_iters_init, critic_iters
+        self.lipschitz_cost = lipschitz_cost
+        self.param_min, self.param_max = param_min, param_max
+        self.solver = torch_ops.make_solver(**dict(self.io, **(solver_kwargs or {})))
+        self.rejections = 0
+
+    # ---- generator --------------------------------------------------------------------
+    def sample_z(self):
+        dim = 2 * self.num_sites
+        return torch.rand((self.local_models, dim, dim), generator=self.rng, device=self.device)
+
+    def tuning_curves(self, rates):
+        return subsample_neurons(rates, self.sample_sites, track_offset_identity=True)
+
+    def generate(self, z, differentiable):
+        """(tuning curves [kept, nb * n_sites], dynamics_penalty, rate_penalty)."""
+        ctx = torch.enable_grad() if differentiable else torch.no_grad()
+        with ctx:
+            if self.mode == 'fixed_point':
+                R, status, _ = torch_ops.ssn_fixed_point(z, self.J, self.D, self.S, self.exts, solver=self.solver)
+                ok = (status == 0).all(dim=1)                      # rejection of non-convergent networks
+                self.rejections += int((~ok).sum())
+                zero = R.new_zeros(())
+                return self.tuning_curves(R[ok]), zero, zero
+            avg, dyn, rate = torch_ops.euler_ssn(
+                z, self.J, self.D, self.S, self.exts, rate_penalty_threshold=self.costs['rate_penalty_threshold'],
+                **dict(self.euler, **self.io))
+            return self.tuning_curves(avg), dyn, rate
+
+    # ---- training steps -----------------------------------------------------------------
+    def next_minibatch(self, n):
+        idx = torch.randint(0, self.data.shape[0], (n,), generator=self.rng, device=self.device)
+        return self.data[idx]
+
+    def train_discriminator(self):
+        fake, _, _ = self.generate(self.sample_z(), differentiable=False)
+        real = self.next_minibatch(max(len(fake), 1))
+        self.opt_disc.zero_grad(set_to_none=True)
+        loss, accuracy = critic_loss(self.critic, fake.float(), real, self.lipschitz_cost, self.rng)
+        loss.backward()
+        rank, world = sdist.world()
+        if world > 1:
+            for p in self.critic.parameters():
+                torch.distributed.all_reduce(p.grad)
+                p.grad /= world
+        self.opt_disc.step()
+        return dict(is_discriminator=True, disc_loss=float(loss.detach()), accuracy=float(accuracy))
+
+    def train_generator(self):
+        tc, dyn, rate = self.generate(self.sample_z(), differentiable=True)
+        loss = -self.critic(tc.float()).mean() + self.costs['dynamics_cost'] * dyn + self.costs['rate_cost'] * rate
+        self.opt_gen.zero_grad(set_to_none=True)
+        for p in self.critic.parameters():
+            p.requires_grad_(False)
+        loss.backward()
+        for p in self.critic.parameters():
+            p.requires_grad_(True)
+        rank, world = sdist.world()
+        dJ, dD, dS = sdist.allreduce_generator_grads(self.J.grad, self.D.grad, self.S.grad)
+        self.J.grad, self.D.grad, self.S.grad = dJ / world, dD / world, dS / world
+        self.opt_gen.step()
+        with torch.no_grad():
+            for p in (self.J, self.D, self.S):
+                p.clamp_(self.param_min, self.param_max)
+        return dict(is_discriminator=False, gen_loss=float(loss.detach()), dynamics_penalty=float(dyn.detach()),
+                    rate_penalty=float(rate.detach()))
+
+    def learning(self):
+        """Generator of per-step info dicts, as BPTTWassersteinGAN.learning (wgan.py:439-444)."""
+        gen_step, critic_iters = 0, self.critic_iters_init
+        while True:
+            for disc_step in range(critic_iters):
+                yield dict(self.train_discriminator(), gen_step=gen_step, disc_step=disc_step)
+            yield dict(self.train_generator(), gen_step=gen_step)
+            gen_step, critic_iters = gen_step + 1, self.critic_iters
