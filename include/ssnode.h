@@ -129,13 +129,15 @@ SSN_API int ssn_fixed_point_batch_f64(const ssn_solver *solver, int nz, int nb, 
  *            zeroed by this call)
  *   mu       float32 [nz][nb][2N] out, may be NULL
  *   status   int32 [nz][nb] out (0 converged / 1 max_iter), iters likewise; may be NULL
- *   rtol     stop when max|d mu| < rtol * max(1, max|g|) per (network, stimulus)
+ *   rtol     stop when max|d mu| < rtol * max|g| per (network, stimulus)
+ *   grad_ext float32 [nz][nb][2N] out, may be NULL: dL/d ext = Phi mu (the gradient w.r.t. the stimulus
+ *            input, needed by the heterogeneous-input generators, networks/ssn.py:645-727)
  */
 SSN_API int ssn_ift_gradient_batch(const ssn_solver *solver, int nz, int nb, int n_sites,
                            const float *z, const ssn_jds *jds, const float *ext,
                            int ext_per_network, const float *R, const float *g,
                            double rtol, double *grad, float *mu, int *status, int *iters,
-                           int mem, void *stream);
+                           float *grad_ext, int mem, void *stream);
 
 /*
  * Unrolled Euler dynamics r_{t+1} = (1-eps) r_t + eps f(W r_t + I), r_0 = 0,
@@ -161,13 +163,14 @@ SSN_API int ssn_euler_forward(const ssn_solver *solver, int nz, int nb, int n_si
  * scalar weights dL/d(dynamics sum), dL/d(rate sum), returns dL/dJ, dL/dD,
  * dL/dS in grad[12] (float64, device, zeroed here).  `traj` and `gain` are the
  * arrays the forward call stored; `adj` is scratch of the same size as traj.
+ * grad_ext (float32 [nz][nb][2N], may be NULL) receives dL/d ext = sum_t gain[t] * lambda_{t+1}.
  */
 SSN_API int ssn_euler_backward(const ssn_solver *solver, int nz, int nb, int n_sites,
                        const float *z, const ssn_jds *jds,
                        int seqlen, int skip_steps, double rate_penalty_threshold,
                        const float *grad_time_avg, double w_dyn, double w_rate,
                        const float *traj, const float *gain, float *adj,
-                       double *grad, void *stream);
+                       double *grad, float *grad_ext, void *stream);
 
 /* Build W [nz][2N][2N] (float32) from z on the device (weight_gen.py:13-26). */
 SSN_API int ssn_generate_weight(int nz, int n_sites, const float *z, const ssn_jds *jds,

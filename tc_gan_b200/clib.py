@@ -104,7 +104,7 @@ libssnode.ssn_fixed_point_batch_f64.restype = c_int
 
 libssnode.ssn_ift_gradient_batch.argtypes = [
     POINTER(SolverStruct), c_int, c_int, c_int, c_void_p, POINTER(JDSStruct), c_void_p, c_int,
-    c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
 libssnode.ssn_ift_gradient_batch.restype = c_int
 
 libssnode.ssn_euler_forward.argtypes = [
@@ -115,7 +115,7 @@ libssnode.ssn_euler_forward.restype = c_int
 libssnode.ssn_euler_backward.argtypes = [
     POINTER(SolverStruct), c_int, c_int, c_int, c_void_p, POINTER(JDSStruct),
     c_int, c_int, c_double, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p,
-    c_void_p, c_void_p]
+    c_void_p, c_void_p, c_void_p]
 libssnode.ssn_euler_backward.restype = c_int
 
 libssnode.ssn_generate_weight.argtypes = [c_int, c_int, c_void_p, POINTER(JDSStruct), c_void_p,

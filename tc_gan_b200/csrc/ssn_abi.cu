@@ -394,7 +394,7 @@ int ssn_generate_weight(int nz, int n_sites, const float *z, const ssn_jds *jds,
 int ssn_ift_gradient_batch(const ssn_solver *solver, int nz, int nb, int n_sites, const float *z,
                            const ssn_jds *jds, const float *ext, int ext_per_network, const float *R,
                            const float *g, double rtol, double *grad, float *mu, int *status, int *iters,
-                           int mem, void *stream) {
+                           float *grad_ext, int mem, void *stream) {
     int rc = validate(solver, nz, nb, n_sites);
     if (rc) return rc;
     if (!jds) { set_error("jds is NULL"); return -1; }
@@ -403,7 +403,7 @@ int ssn_ift_gradient_batch(const ssn_solver *solver, int nz, int nb, int n_sites
     if ((rc = next_counter(&counter))) return rc;
     if (mem == SSN_MEM_DEVICE)
         return launch_ift_gradient(*solver, nz, nb, n_sites, z, *jds, ext, ext_per_network, R, g, rtol, grad, mu,
-                                   status, iters, counter, (cudaStream_t)stream);
+                                   status, iters, grad_ext, counter, (cudaStream_t)stream);
     if ((rc = tl_ctx.ensure_device())) return rc;
     cudaStream_t st = tl_ctx.stream;
     const size_t nR = (size_t)nz * nb * dim, nE = (size_t)(ext_per_network ? nz : 1) * nb * dim;
@@ -414,15 +414,17 @@ int ssn_ift_gradient_batch(const ssn_solver *solver, int nz, int nb, int n_sites
     GET(12, int, (size_t)nz * nb * 2, ds);
     GET(13, float, nR, dmu);
     GET(14, double, 12, dgrad);
+    GET(15, float, nR, dge);
     SSN_CUDA(cudaMemcpyAsync(dz, z, (size_t)nz * dim * dim * sizeof(float), cudaMemcpyHostToDevice, st));
     SSN_CUDA(cudaMemcpyAsync(de, ext, nE * sizeof(float), cudaMemcpyHostToDevice, st));
     SSN_CUDA(cudaMemcpyAsync(dr, R, nR * sizeof(float), cudaMemcpyHostToDevice, st));
     SSN_CUDA(cudaMemcpyAsync(dg, g, nR * sizeof(float), cudaMemcpyHostToDevice, st));
     rc = launch_ift_gradient(*solver, nz, nb, n_sites, dz, *jds, de, ext_per_network, dr, dg, rtol, dgrad, dmu, ds,
-                             ds + (size_t)nz * nb, counter, st);
+                             ds + (size_t)nz * nb, grad_ext ? dge : nullptr, counter, st);
     if (rc) return rc;
     SSN_CUDA(cudaMemcpyAsync(grad, dgrad, 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (mu) SSN_CUDA(cudaMemcpyAsync(mu, dmu, nR * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (grad_ext) SSN_CUDA(cudaMemcpyAsync(grad_ext, dge, nR * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (status) SSN_CUDA(cudaMemcpyAsync(status, ds, (size_t)nz * nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (iters)
         SSN_CUDA(cudaMemcpyAsync(iters, ds + (size_t)nz * nb, (size_t)nz * nb * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -449,14 +451,14 @@ int ssn_euler_forward(const ssn_solver *solver, int nz, int nb, int n_sites, con
 int ssn_euler_backward(const ssn_solver *solver, int nz, int nb, int n_sites, const float *z, const ssn_jds *jds,
                        int seqlen, int skip_steps, double rate_penalty_threshold, const float *grad_time_avg,
                        double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
-                       double *grad, void *stream) {
+                       double *grad, float *grad_ext, void *stream) {
     int rc = validate(solver, nz, nb, n_sites);
     if (rc) return rc;
     if (!jds || !traj || !gain || !adj) { set_error("euler backward needs jds, traj, gain, adj"); return -1; }
     int *counter = nullptr;
     if ((rc = next_counter(&counter))) return rc;
     return launch_euler_backward(*solver, nz, nb, n_sites, z, *jds, seqlen, skip_steps, rate_penalty_threshold,
-                                 grad_time_avg, w_dyn, w_rate, traj, gain, adj, grad, counter,
+                                 grad_time_avg, w_dyn, w_rate, traj, gain, adj, grad, grad_ext, counter,
                                  (cudaStream_t)stream);
 }
 

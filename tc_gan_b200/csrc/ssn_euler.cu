@@ -40,7 +40,7 @@ struct EulerArgs {
     const float *g_avg;
     double w_dyn, w_rate;
     const float *traj_in, *gain_in;
-    float *adj;
+    float *adj, *grad_ext;
 };
 
 template <int TI, int KL, int NWARPS, bool BACKWARD>
@@ -179,10 +179,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                     if (valid[u] && active) a.time_avg[(size_t)net * slice + goff[u]] = (float)(avg[u] / T);
             } else {
                 // ---- adjoint recursion, k = seqlen .. 1 (array index tp = k - 1) ----
-                float gavg[TO], r_cur[TO], r_next[TO];
+                float gavg[TO], r_cur[TO], r_next[TO], gext[TO];
 #pragma unroll
                 for (int u = 0; u < TO; ++u) {
-                    gavg[u] = 0.f; r_cur[u] = 0.f; r_next[u] = 0.f;
+                    gavg[u] = 0.f; r_cur[u] = 0.f; r_next[u] = 0.f; gext[u] = 0.f;
                     if (valid[u] && active) {
                         gavg[u] = __ldg(a.g_avg + (size_t)net * slice + goff[u]) / (float)T;
                         r_cur[u] = __ldg(a.traj_in + net_base + (size_t)(seqlen - 1) * slice + goff[u]);
@@ -220,9 +220,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                             state[u] = lam;                           // lambda_k
                             // q_{k-1} = gain[k-1] * lambda_k, paired with r_{k-1} = traj[tp-1]
                             float q = 0.f;
-                            if (active && tp > 0) {
+                            if (active) {
                                 q = __ldg(a.gain_in + net_base + (size_t)tp * slice + goff[u]) * (float)lam;
-                                a.adj[net_base + (size_t)(tp - 1) * slice + goff[u]] = q;
+                                gext[u] += q;                             // dL/d ext = sum_k q_k, q_0 included
+                                if (tp > 0) a.adj[net_base + (size_t)(tp - 1) * slice + goff[u]] = q;
+                                else q = 0.f;                             // q_0 pairs with r_0 = 0: nothing to publish
                             }
                             if (active && tp == seqlen - 1)
                                 a.adj[net_base + (size_t)tp * slice + goff[u]] = 0.f;   // q_seqlen = 0
@@ -235,6 +237,11 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                         }
                     cluster.sync();
                     buf = nbuf;
+                }
+                if (a.grad_ext) {
+#pragma unroll
+                    for (int u = 0; u < TO; ++u)
+                        if (valid[u] && active) a.grad_ext[(size_t)net * slice + goff[u]] = gext[u];
                 }
             }
             cluster.sync();
@@ -390,13 +397,13 @@ int launch_euler_forward(const ssn_solver &sv, int nz, int nb, int n_sites, cons
 int launch_euler_backward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                           int seqlen, int skip_steps, double threshold, const float *grad_time_avg,
                           double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
-                          double *grad, int *counter, cudaStream_t stream) {
+                          double *grad, float *grad_ext, int *counter, cudaStream_t stream) {
     SSN_CUDA(cudaMemsetAsync(grad, 0, 12 * sizeof(double), stream));
     if (nz <= 0 || nb <= 0) return 0;
     EulerArgs a = {};
     fill_common(a, sv, nz, nb, n_sites, z, jds, seqlen, skip_steps, threshold);
     a.g_avg = grad_time_avg; a.w_dyn = w_dyn; a.w_rate = w_rate;
-    a.traj_in = traj; a.gain_in = gain; a.adj = adj;
+    a.traj_in = traj; a.gain_in = gain; a.adj = adj; a.grad_ext = grad_ext;
     int rc = launch_euler(true, a, n_sites, nz, counter, stream);
     if (rc) return rc;
     const int dim = 2 * n_sites, tiles = (dim + GT - 1) / GT;

@@ -27,7 +27,7 @@ struct IftArgs {
     const float *ext;
     long long ext_stride_z;
     const float *R, *g;
-    float *mu;
+    float *mu, *grad_ext;
     int *status, *iters;
     double *grad;                  // [12] J, D, S
     int *work_counter;
@@ -211,7 +211,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
             // ---------- results of the solve ----------
 #pragma unroll
             for (int u = 0; u < TO; ++u)
-                if (valid[u] && active && a.mu) a.mu[sol * dim + row_base + own0 + u] = (float)mu[u];
+                if (valid[u] && active) {
+                    if (a.mu) a.mu[sol * dim + row_base + own0 + u] = (float)mu[u];
+                    if (a.grad_ext) a.grad_ext[sol * dim + row_base + own0 + u] = (float)((double)phi[u] * mu[u]);
+                }
             if (rank == 0 && tid < KL && (kl % Own::SPLIT) == 0 && active) {
                 if (a.status) a.status[sol] = my_status;
                 if (a.iters) a.iters[sol] = my_iters;
@@ -289,7 +292,8 @@ bool choose_cluster_shape(int n_sites, ClusterShape *out, int smem_limit, int *v
 
 int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                         const float *ext, int ext_per_network, const float *R, const float *g, double rtol,
-                        double *grad, float *mu, int *status, int *iters, int *counter, cudaStream_t stream) {
+                        double *grad, float *mu, int *status, int *iters, float *grad_ext, int *counter,
+                        cudaStream_t stream) {
     SSN_CUDA(cudaMemsetAsync(grad, 0, 12 * sizeof(double), stream));
     if (nz <= 0 || nb <= 0) return 0;
     int dev = 0, limit = 0, variant = 0;
@@ -306,7 +310,7 @@ int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const
     a.nz = nz; a.nb = nb; a.n_sites = n_sites;
     a.z = z; a.wc = make_weight_const(jds, n_sites);
     a.ext = ext; a.ext_stride_z = ext_per_network ? (long long)nb * 2 * n_sites : 0;
-    a.R = R; a.g = g; a.mu = mu; a.status = status; a.iters = iters; a.grad = grad; a.work_counter = counter;
+    a.R = R; a.g = g; a.mu = mu; a.grad_ext = grad_ext; a.status = status; a.iters = iters; a.grad = grad; a.work_counter = counter;
     a.io = make_io_const<float>(sv.io_type, sv.k, sv.n, sv.rate_soft_bound, sv.rate_hard_bound);
     a.eps_E = sv.dt / sv.tau_E; a.eps_I = sv.dt / sv.tau_I;
     a.rtol = rtol > 0 ? rtol : 1e-6;

@@ -19,7 +19,8 @@ int regw_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *re
 
 int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                         const float *ext, int ext_per_network, const float *R, const float *g, double rtol,
-                        double *grad, float *mu, int *status, int *iters, int *counter, cudaStream_t stream);
+                        double *grad, float *mu, int *status, int *iters, float *grad_ext, int *counter,
+                        cudaStream_t stream);
 
 int launch_euler_forward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                          const float *ext, int ext_per_network, int seqlen, int skip_steps, double threshold,
@@ -28,7 +29,7 @@ int launch_euler_forward(const ssn_solver &sv, int nz, int nb, int n_sites, cons
 int launch_euler_backward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                           int seqlen, int skip_steps, double threshold, const float *grad_time_avg,
                           double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
-                          double *grad, int *counter, cudaStream_t stream);
+                          double *grad, float *grad_ext, int *counter, cudaStream_t stream);
 
 int launch_generate_weight(int nz, int n_sites, const float *z, const ssn_jds &jds, float *W, cudaStream_t stream);
 int launch_convert_f64_to_f32(const double *src, float *dst, size_t n, cudaStream_t stream);

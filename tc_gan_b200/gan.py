@@ -80,9 +80,15 @@ class SSNWassersteinGAN(object):
                  critic_layers=(128, 128), layer_norm=False,
                  critic_iters_init=50, critic_iters=5, lipschitz_cost=10.0,
                  gen_learning_rate=0.001, disc_learning_rate=0.001,
-                 param_min=1e-3, param_max=10.0, seed=0, device='cuda', solver_kwargs=None):
+                 param_min=1e-3, param_max=10.0, seed=0, device='cuda', solver_kwargs=None,
+                 ssn_type='default', V=0.5, dist_in='bernoulli', V_min=0.0, V_max=1.0):
         if mode not in ('fixed_point', 'bptt'):
             raise ValueError('Unknown mode: {}'.format(mode))
+        if ssn_type not in ('default', 'heteroin', 'deg-heteroin'):
+            raise ValueError('Unknown ssn_type: {}'.format(ssn_type))
+        if dist_in not in ('bernoulli', 'uniform'):
+            raise ValueError('Unknown dist_in: {}'.format(dist_in))
+        self.ssn_type, self.dist_in, self.V_min, self.V_max = ssn_type, dist_in, V_min, V_max
         self.mode, self.num_sites, self.num_models = mode, int(num_sites), int(num_models)
         self.device = torch.device(device)
         jds = ssnode.new_JDS()
@@ -99,7 +105,13 @@ class SSNWassersteinGAN(object):
         assert self.data.shape[1] == n_in, (self.data.shape, n_in)
         torch.manual_seed(seed)
         self.critic = Critic(n_in, critic_layers, layer_norm).to(self.device)
-        self.opt_gen = torch.optim.Adam([self.J, self.D, self.S], lr=gen_learning_rate, betas=(0.5, 0.9))
+        # heterogeneous input (networks/ssn.py:645-727): V is a generator parameter, 2-vector or scalar
+        self.V = None
+        if ssn_type != 'default':
+            v0 = np.broadcast_to(np.asarray(V, dtype=float), (2,)).copy() if ssn_type == 'heteroin' else float(np.asarray(V))
+            self.V = torch.tensor(v0, dtype=torch.float64, device=self.device, requires_grad=True)
+        self.gen_params = [self.J, self.D, self.S] + ([self.V] if self.V is not None else [])
+        self.opt_gen = torch.optim.Adam(self.gen_params, lr=gen_learning_rate, betas=(0.5, 0.9))
         self.opt_disc = torch.optim.Adam(self.critic.parameters(), lr=disc_learning_rate, betas=(0.5, 0.9))
         self.rng = torch.Generator(device=self.device)
         rank, world = sdist.world()
@@ -123,18 +135,30 @@ class SSNWassersteinGAN(object):
     def tuning_curves(self, rates):
         return subsample_neurons(rates, self.sample_sites, track_offset_identity=True)
 
+    def stimulus(self, nz):
+        """[nb, 2N], or [nz, nb, 2N] scaled per neuron by 1 + V z_in for the heteroin types."""
+        if self.V is None:
+            return self.exts
+        shape = (nz, 2 * self.num_sites)
+        if self.dist_in == 'bernoulli':
+            zs_in = torch.randint(0, 2, shape, generator=self.rng, device=self.device).float() * 2 - 1
+        else:
+            zs_in = torch.rand(shape, generator=self.rng, device=self.device) * 2 - 1
+        return torch_ops.hetero_input(self.exts, zs_in, self.V)
+
     def generate(self, z, differentiable):
         """(tuning curves [kept, nb * n_sites], dynamics_penalty, rate_penalty)."""
         ctx = torch.enable_grad() if differentiable else torch.no_grad()
         with ctx:
+            exts = self.stimulus(z.shape[0])
             if self.mode == 'fixed_point':
-                R, status, _ = torch_ops.ssn_fixed_point(z, self.J, self.D, self.S, self.exts, solver=self.solver)
+                R, status, _ = torch_ops.ssn_fixed_point(z, self.J, self.D, self.S, exts, solver=self.solver)
                 ok = (status == 0).all(dim=1)                      # rejection of non-convergent networks
                 self.rejections += int((~ok).sum())
                 zero = R.new_zeros(())
                 return self.tuning_curves(R[ok]), zero, zero
             avg, dyn, rate = torch_ops.euler_ssn(
-                z, self.J, self.D, self.S, self.exts, rate_penalty_threshold=self.costs['rate_penalty_threshold'],
+                z, self.J, self.D, self.S, exts, rate_penalty_threshold=self.costs['rate_penalty_threshold'],
                 **dict(self.euler, **self.io))
             return self.tuning_curves(avg), dyn, rate
 
@@ -169,10 +193,15 @@ class SSNWassersteinGAN(object):
         rank, world = sdist.world()
         dJ, dD, dS = sdist.allreduce_generator_grads(self.J.grad, self.D.grad, self.S.grad)
         self.J.grad, self.D.grad, self.S.grad = dJ / world, dD / world, dS / world
+        if self.V is not None and world > 1:
+            torch.distributed.all_reduce(self.V.grad)
+            self.V.grad /= world
         self.opt_gen.step()
         with torch.no_grad():
             for p in (self.J, self.D, self.S):
                 p.clamp_(self.param_min, self.param_max)
+            if self.V is not None:
+                self.V.clamp_(self.V_min, self.V_max)
         return dict(is_discriminator=False, gen_loss=float(loss.detach()), dynamics_penalty=float(dyn.detach()),
                     rate_penalty=float(rate.detach()))
 

@@ -69,8 +69,9 @@ def fixed_points(z, J, D, S, ext, solver=None, r_init=None, precise=False):
     return R, status, iters
 
 
-def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-6, return_mu=False):
-    """dL/d(J, D, S) (three float64 [2, 2] CUDA tensors) from dL/dR at the fixed points R."""
+def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-6, return_mu=False, return_grad_ext=False):
+    """dL/d(J, D, S) (three float64 [2, 2] CUDA tensors) from dL/dR at the fixed points R;
+    with return_grad_ext also dL/d ext [nz, nb, 2N] (= Phi mu, for heterogeneous-input generators)."""
     _check_cuda(z, ext, R, grad_R)
     solver = solver or make_solver()
     z32, e32, R32, g32 = _f32c(z), _f32c(ext), _f32c(R), _f32c(grad_R)
@@ -78,17 +79,22 @@ def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-6, return_mu=F
     nb = R32.shape[1]
     grad = torch.empty(12, dtype=torch.float64, device=z.device)
     mu = torch.empty_like(R32) if return_mu else None
+    gext = torch.zeros_like(R32) if return_grad_ext else None
     status = torch.empty((nz, nb), dtype=torch.int32, device=z.device)
     iters = torch.empty((nz, nb), dtype=torch.int32, device=z.device)
     with torch.cuda.device(z.device):
         clib.check_call(libssnode.ssn_ift_gradient_batch(
             solver, nz, nb, dim // 2, z32.data_ptr(), _jds_struct(J, D, S), e32.data_ptr(), int(e32.dim() == 3),
             R32.data_ptr(), g32.data_ptr(), float(rtol), grad.data_ptr(), None if mu is None else mu.data_ptr(),
-            status.data_ptr(), iters.data_ptr(), clib.MEM_DEVICE, _stream()), 'ssn_ift_gradient_batch')
+            status.data_ptr(), iters.data_ptr(), None if gext is None else gext.data_ptr(),
+            clib.MEM_DEVICE, _stream()), 'ssn_ift_gradient_batch')
     dJ, dD, dS = grad[0:4].reshape(2, 2), grad[4:8].reshape(2, 2), grad[8:12].reshape(2, 2)
+    out = (dJ, dD, dS)
     if return_mu:
-        return dJ, dD, dS, mu, status, iters
-    return dJ, dD, dS
+        out = out + (mu, status, iters)
+    if return_grad_ext:
+        out = out + (gext,)
+    return out
 
 
 class SSNFixedPoint(torch.autograd.Function):
@@ -105,9 +111,15 @@ class SSNFixedPoint(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_R, _gs, _gi):
         z, J, D, S, ext, R = ctx.saved_tensors
-        dJ, dD, dS = ift_gradient(z, J, D, S, ext, R, grad_R, solver=ctx.solver)
+        need_ext = ctx.needs_input_grad[4]
+        res = ift_gradient(z, J, D, S, ext, R, grad_R, solver=ctx.solver, return_grad_ext=need_ext)
+        dJ, dD, dS = res[:3]
+        g_ext = None
+        if need_ext:
+            g_ext = res[3] if ext.dim() == 3 else res[3].sum(dim=0)
+            g_ext = g_ext.to(ext.dtype)
         return (None, dJ.to(J.dtype).to(J.device), dD.to(D.dtype).to(D.device), dS.to(S.dtype).to(S.device),
-                None, None, None)
+                g_ext, None, None)
 
 
 def ssn_fixed_point(z, J, D, S, ext, solver=None, precise=False):
@@ -142,7 +154,7 @@ class EulerSSN(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, J, D, S, ext, seqlen, skip_steps, solver, threshold):
-        need_grad = any(ctx.needs_input_grad[1:4])
+        need_grad = any(ctx.needs_input_grad[1:5])
         time_avg, pen, traj, gain = euler_forward(z, J, D, S, ext, seqlen, skip_steps, solver, threshold,
                                                   store=need_grad)
         nz, nb, dim = time_avg.shape
@@ -152,13 +164,14 @@ class EulerSSN(torch.autograd.Function):
         dyn = (pen[0] / n_dyn).to(torch.float32)
         rate = (pen[1] / n_rate).to(torch.float32)
         ctx.save_for_backward(z, J, D, S, traj, gain)
-        ctx.meta = (seqlen, skip_steps, solver, threshold, n_dyn, n_rate)
+        ctx.meta = (seqlen, skip_steps, solver, threshold, n_dyn, n_rate, ext.dim(), ext.dtype)
         return time_avg, dyn, rate
 
     @staticmethod
     def backward(ctx, g_avg, g_dyn, g_rate):
         z, J, D, S, traj, gain = ctx.saved_tensors
-        seqlen, skip_steps, solver, threshold, n_dyn, n_rate = ctx.meta
+        seqlen, skip_steps, solver, threshold, n_dyn, n_rate, ext_dim, ext_dtype = ctx.meta
+        need_ext = ctx.needs_input_grad[4]
         nz, _, nb, dim = traj.shape
         dev = traj.device
         g32 = _f32c(g_avg) if g_avg is not None else torch.zeros((nz, nb, dim), dtype=torch.float32, device=dev)
@@ -166,14 +179,18 @@ class EulerSSN(torch.autograd.Function):
         w_rate = float(g_rate) / n_rate if g_rate is not None else 0.0
         adj = torch.empty_like(traj)
         grad = torch.empty(12, dtype=torch.float64, device=dev)
+        gext = torch.zeros((nz, nb, dim), dtype=torch.float32, device=dev) if need_ext else None
         with torch.cuda.device(dev):
             clib.check_call(libssnode.ssn_euler_backward(
                 solver, nz, nb, dim // 2, _f32c(z).data_ptr(), _jds_struct(J, D, S), int(seqlen), int(skip_steps),
                 float(threshold), g32.data_ptr(), w_dyn, w_rate, traj.data_ptr(), gain.data_ptr(), adj.data_ptr(),
-                grad.data_ptr(), _stream()), 'ssn_euler_backward')
+                grad.data_ptr(), None if gext is None else gext.data_ptr(), _stream()), 'ssn_euler_backward')
         dJ, dD, dS = grad[0:4].reshape(2, 2), grad[4:8].reshape(2, 2), grad[8:12].reshape(2, 2)
+        g_ext = None
+        if need_ext:
+            g_ext = (gext if ext_dim == 3 else gext.sum(dim=0)).to(ext_dtype)
         return (None, dJ.to(J.dtype).to(J.device), dD.to(D.dtype).to(D.device), dS.to(S.dtype).to(S.device),
-                None, None, None, None, None)
+                g_ext, None, None, None, None)
 
 
 def euler_ssn(z, J, D, S, ext, seqlen=1200, skip_steps=1000, dt=0.1, tau_E=10.0, tau_I=1.0,
@@ -189,6 +206,20 @@ def euler_ssn(z, J, D, S, ext, seqlen=1200, skip_steps=1000, dt=0.1, tau_E=10.0,
                               rate_soft_bound=rate_soft_bound, rate_hard_bound=rate_hard_bound,
                               rate_stop_at=rate_hard_bound)
     return EulerSSN.apply(z, J, D, S, ext, int(seqlen), int(skip_steps), solver, float(rate_penalty_threshold))
+
+
+def hetero_input(ext, zs_in, V):
+    """
+    Heterogeneous stimulus of tc_gan.networks.ssn.HeteroInputWrapper (networks/ssn.py:645-727):
+    stimulus[z, b, i] = (1 + V_pop(i) * zs_in[z, i]) * ext[b, i].  `V` is a 2-vector (E, I;
+    ssn_type 'heteroin') or a scalar ('deg-heteroin'); `zs_in` [nz, 2N] is +-1 (bernoulli) or
+    uniform in [-1, 1].  Differentiable w.r.t. V (the kernels return dL/d ext).
+    """
+    n_sites = ext.shape[-1] // 2
+    V = torch.as_tensor(V, device=ext.device) if not torch.is_tensor(V) else V
+    vpop = V.expand(2) if V.dim() == 0 else V
+    vs = torch.cat([vpop[0].expand(n_sites), vpop[1].expand(n_sites)]).to(ext.dtype)
+    return (1 + vs[None, None, :] * zs_in.to(ext.dtype)[:, None, :]) * ext[None]
 
 
 def smoke(oracle):

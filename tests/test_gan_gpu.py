@@ -37,6 +37,19 @@ def test_single_generator_step(mode):
     assert g.sample_sites == [5, 10, 15]
 
 
+@pytest.mark.parametrize('mode,ssn_type', [('bptt', 'deg-heteroin'), ('fixed_point', 'heteroin')])
+def test_heteroin_generator_step(mode, ssn_type):
+    """The paper's runs use ssn_type 'deg-heteroin' (scripts/fig4/gan/run.json): V is learned too."""
+    g = make_gan(mode, ssn_type=ssn_type, V=0.5, dist_in='bernoulli' if mode == 'bptt' else 'uniform')
+    V0 = g.V.detach().clone()
+    for info in g.learning():
+        if not info['is_discriminator']:
+            break
+    assert np.isfinite(info['gen_loss'])
+    assert g.V.shape == (V0.shape) and not np.allclose(g.V.detach().cpu().numpy(), V0.cpu().numpy())
+    assert (g.V >= 0).all() and (g.V <= 1).all()
+
+
 def test_generator_gradient_matches_finite_differences():
     import torch
     g = make_gan('fixed_point', num_models=4, solver_kwargs=dict(atol=1e-9, max_iter=200000))

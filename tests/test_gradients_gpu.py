@@ -133,3 +133,53 @@ def test_euler_long_unroll_reaches_fixed_point(ops, oracle):
     R, status, _ = ops.fixed_points(tens(z), J, D, S, tens(exts), solver=solver, precise=True)
     assert (status == 0).all()
     np.testing.assert_allclose(avg.cpu().numpy(), R.cpu().numpy(), rtol=5e-4, atol=5e-4)
+
+
+def test_heterogeneous_input_gradients(ops, oracle):
+    """heteroin / deg-heteroin generators (networks/ssn.py:645-727): stimulus scaled per
+    neuron by 1 + V z_in; dL/dV through both gradient paths against float64 (torch autograd for BPTT,
+    the adjoint formula dL/d ext = Phi mu for the fixed point)."""
+    import torch
+    n_sites, nz, nb, seqlen, skip = 20, 3, 8, 40, 25
+    jds = oracle.new_JDS()
+    exts = oracle.stimulus_input(oracle.DEFAULT_BANDWIDTHS, n_sites)
+    rs = np.random.RandomState(11)
+    z = rs.rand(nz, 2 * n_sites, 2 * n_sites).astype(np.float32).astype(np.float64)
+    zs_in = rs.choice(2, (nz, 2 * n_sites)) * 2.0 - 1.0
+    G = rs.randn(nz, nb, 2 * n_sites)
+    V0 = np.array([0.3, 0.15])
+    # ---- BPTT path, ssn_type 'heteroin' (two-component V) ----
+    t64 = lambda a, g=False: torch.tensor(np.asarray(a), dtype=torch.float64, requires_grad=g)
+    Vo = t64(V0, True)
+    J, D, S = (t64(jds[k], True) for k in 'JDS')
+    vs = torch.cat([Vo[0].expand(n_sites), Vo[1].expand(n_sites)])
+    ext_o = (1 + vs[None, None, :] * t64(zs_in)[:, None, :]) * t64(exts)[None]
+    avg_o, dyn_o, rate_o = oracle.euler_unroll_torch(t64(z), J, D, S, ext_o, seqlen, skip, 0.01, 0.1,
+                                                     rate_penalty_threshold=0.5)
+    ((avg_o * t64(G)).sum() + 3.0 * dyn_o + 2.0 * rate_o).backward()
+    Vg = tens(V0, torch.float64, grad=True)
+    Jg, Dg, Sg = (tens(jds[k], torch.float64, grad=True) for k in 'JDS')
+    ext_g = ops.hetero_input(tens(exts), tens(zs_in), Vg)
+    avg, dyn, rate = ops.euler_ssn(tens(z), Jg, Dg, Sg, ext_g, seqlen=seqlen, skip_steps=skip,
+                                   rate_penalty_threshold=0.5)
+    np.testing.assert_allclose(avg.detach().cpu().numpy(), avg_o.detach().numpy(), rtol=1e-4, atol=1e-5)
+    ((avg * tens(G)).sum() + 3.0 * dyn + 2.0 * rate).backward()
+    np.testing.assert_allclose(Vg.grad.cpu().numpy(), Vo.grad.numpy(), rtol=1e-3, atol=1e-3 * np.abs(Vo.grad.numpy()).max())
+    np.testing.assert_allclose(Jg.grad.cpu().numpy(), J.grad.numpy(), rtol=1e-3, atol=1e-3 * np.abs(J.grad.numpy()).max())
+    # ---- fixed-point path, 'deg-heteroin' (scalar V) ----
+    Vs = tens(0.25, torch.float64, grad=True)
+    Jg, Dg, Sg = (tens(jds[k], torch.float64, grad=True) for k in 'JDS')
+    ext_g = ops.hetero_input(tens(exts), tens(zs_in), Vs)
+    R, status, _ = ops.ssn_fixed_point(tens(z), Jg, Dg, Sg, ext_g)
+    assert (status == 0).all()
+    (R * tens(G)).sum().backward()
+    ext_np = (1 + 0.25 * zs_in[:, None, :]) * exts[None]
+    W = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
+    Rn = R.detach().double().cpu().numpy()
+    dV = 0.0
+    for iz in range(nz):
+        for ib in range(nb):
+            phi = oracle.io_gain(W[iz] @ Rn[iz, ib] + ext_np[iz, ib])
+            mu = np.linalg.solve(np.eye(2 * n_sites) - W[iz].T * phi[None, :], G[iz, ib])
+            dV += np.sum(phi * mu * zs_in[iz] * exts[ib])           # dL/d ext * d ext/dV
+    assert abs(float(Vs.grad) - dV) <= 2e-4 * abs(dV), (float(Vs.grad), dV)
