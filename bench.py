@@ -89,6 +89,18 @@ class ClockSampler(object):
                 'samples': len(sm)}
 
 
+def host_cores():
+    """Threads for the CPU arms: every core this process may run on.  (tc_gan.utils.cpu_count honours
+    OMP_NUM_THREADS, but torchrun exports OMP_NUM_THREADS=1 to its ranks, which would cripple the
+    reference arm; SSN_BASELINE_THREADS overrides.)"""
+    if os.environ.get('SSN_BASELINE_THREADS'):
+        return max(1, int(os.environ['SSN_BASELINE_THREADS']))
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
     """The reference's own CPU implementation on the host cores (rank 0 only)."""
     rank = int(os.environ.get('RANK', '0'))
@@ -97,7 +109,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import numpy as np
     import ssn_oracle as so
-    cores = int(os.environ.get('OMP_NUM_THREADS', 0)) or (os.cpu_count() or 1)
+    cores = host_cores()
     kind = 'reference' if so.ref_lib() is not None else 'port'
     nz = max(8, min(NZ, 32 * cores))            # bounded sample of the 1024-network step (~5 s of CPU work per step)
     jds = so.new_JDS()
@@ -134,7 +146,7 @@ def cpu_baseline(seconds_budget=20.0):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import numpy as np
     import ssn_oracle as so
-    cores = int(os.environ.get('OMP_NUM_THREADS', 0)) or (os.cpu_count() or 1)
+    cores = host_cores()
     kind = 'reference' if so.ref_lib() is not None else 'port'
     nz = max(8, min(NZ, 64 * cores))             # ~10 s of CPU work on all host cores
     jds = so.new_JDS()
