@@ -29,16 +29,15 @@
 
 namespace ssn {
 
-constexpr int RW_TI = 7;                               // rows per warp
 constexpr int RW_MAXC = 16;                            // largest cluster (non-portable size, 4-warp CTAs)
-constexpr int RW_BLOCKS = 64;                          // csize * warps <= 64 panel blocks
+constexpr int RW_BLOCKS = 80;                          // csize * warps <= 80 panel blocks
 constexpr int RW_XE = 4;                               // stimuli refreshed per event
 // State panel: one block per (source CTA, warp): 7 float4 rows of stimuli 0..3, 7 float4 rows of
 // stimuli 4..7, one 16-byte slot whose first word carries the warp's flags.  A warp publishes its
 // block to a peer CTA with ONE cp.async.bulk (one mbarrier transaction per block, not per element).
-constexpr int RW_BLK_SLOTS = 2 * RW_TI + 1, RW_BLK_BYTES = RW_BLK_SLOTS * 16;          // 15 slots, 240 B
-constexpr int RW_ZERO_SLOT = RW_BLOCKS * RW_BLK_SLOTS;                                  // slot 960: always 0
-constexpr int RW_BUF_BYTES = (RW_ZERO_SLOT + 1) * 16;
+// (TI = rows per warp: 7 -> 15 slots, 240 B per block; the slot after the last block is always zero)
+__host__ __device__ constexpr int rw_blk_slots(int ti) { return 2 * ti + 1; }
+__host__ __device__ constexpr int rw_buf_bytes(int ti) { return (RW_BLOCKS * rw_blk_slots(ti) + 1) * 16; }
 constexpr int TAB_PER_UNIT = 8;                        // table nodes per unit of v
 constexpr double TAB_V_MIN = 1.0;
 
@@ -74,10 +73,10 @@ struct RwMisc {
     unsigned pdelta[RW_MAXC];
     int next_net;
 };
-__host__ __device__ inline RwSmem rw_smem_layout(int kpad, int n_sites, int tab_nodes, int nt) {
+__host__ __device__ inline RwSmem rw_smem_layout(int kpad, int n_sites, int tab_nodes, int nt, int ti) {
     RwSmem L;
     int o = 0;
-    L.x_off = o;    o += 2 * RW_BUF_BYTES;             // [buf][source CTA][warp] blocks of RW_BLK_BYTES + a zero slot
+    L.x_off = o;    o += 2 * rw_buf_bytes(ti);         // [buf][source CTA][warp] blocks + a zero slot
     L.xe_off = o;   o += 2 * RW_XE * kpad * 4;         // exact-pass columns: hi[4][kpad], lo[4][kpad]
     L.tab_off = o;  o += tab_nodes * 32;               // cubic table of f: 4 doubles per node
     L.gtab_off = o; o += ((4 * n_sites * 4 + 15) / 16) * 16;
@@ -184,14 +183,18 @@ __device__ __forceinline__ double io_eval_common(const RwArgs &a, const double *
     return f;
 }
 
-template <int NC, int NW>
+template <int NC, int NW, int TI>
 __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(const RwArgs a) {
-    constexpr int RW_WARPS = NW, RW_THREADS = 32 * NW;
+    constexpr int RW_WARPS = NW, RW_THREADS = 32 * NW, RW_TI = TI, NP = TI / 2;
+    constexpr bool ODD = (TI & 1) != 0;                   // a single (unpaired) last row
+    constexpr int RW_BLK_SLOTS = rw_blk_slots(TI), RW_BLK_BYTES = RW_BLK_SLOTS * 16;
+    constexpr int RW_ZERO_SLOT = RW_BLOCKS * RW_BLK_SLOTS, RW_BUF_BYTES = rw_buf_bytes(TI);
+    static_assert(TI >= 2 && TI <= 8, "rows per warp");
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int csize = a.csize, dim = a.dim, kpad = a.kpad, rpc = a.rpc, N = a.n_sites;
-    const RwSmem L = rw_smem_layout(kpad, N, a.tab_nodes, RW_THREADS);
+    const RwSmem L = rw_smem_layout(kpad, N, a.tab_nodes, RW_THREADS, TI);
     float *Xf = reinterpret_cast<float *>(smem + L.x_off);
     float *xe = reinterpret_cast<float *>(smem + L.xe_off);
     double *tab = reinterpret_cast<double *>(smem + L.tab_off);
@@ -277,8 +280,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
         if (net >= a.nz) break;
 
         // ---- W tile -> registers ----
-        unsigned long long wp[3][NC];                              // rows (0,1), (2,3), (4,5) as packed pairs
-        float ws[NC];                                              // row 6
+        unsigned long long wp[NP][NC];                             // rows (0,1), (2,3), ... as packed pairs
+        float ws[ODD ? NC : 1];                                    // the unpaired last row (odd TI)
         {
             // all 7 x NC loads are issued before any is consumed (one round trip to L2/HBM, not 98)
             const float *src = a.w + (size_t)net * dim * dim + (size_t)(row_base + row0) * dim + lane;
@@ -306,10 +309,9 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
             }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                wp[0][c] = pack2(zv[0][c], zv[1][c]);
-                wp[1][c] = pack2(zv[2][c], zv[3][c]);
-                wp[2][c] = pack2(zv[4][c], zv[5][c]);
-                ws[c] = zv[6][c];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) wp[q][c] = pack2(zv[2 * q][c], zv[2 * q + 1][c]);
+                if (ODD) ws[c] = zv[TI - 1][c];
             }
         }
 
@@ -365,9 +367,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                 unsigned F;
                 {
                     const unsigned char *xb = smem + L.x_off + buf * RW_BUF_BYTES + 2 * RW_TI * 16;
-                    F = __reduce_or_sync(0xffffffffu,
-                                         *reinterpret_cast<const unsigned *>(xb + lane * RW_BLK_BYTES) |
-                                         *reinterpret_cast<const unsigned *>(xb + (lane + 32) * RW_BLK_BYTES));
+                    unsigned f = *reinterpret_cast<const unsigned *>(xb + lane * RW_BLK_BYTES) |
+                                 *reinterpret_cast<const unsigned *>(xb + (lane + 32) * RW_BLK_BYTES);
+                    if (lane + 64 < RW_BLOCKS) f |= *reinterpret_cast<const unsigned *>(xb + (lane + 64) * RW_BLK_BYTES);
+                    F = __reduce_or_sync(0xffffffffu, f);
                 }
                 if (a.dbg & 1) F = 0x00ff00ffu;          // timing experiment: no exchange, nobody converges or refreshes
                 if (it > 1) {
@@ -428,10 +431,9 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                             const double h = (double)xh[c * 32 + lane];
                             const float l = xl[c * 32 + lane];
                             float wv[RW_TI];
-                            unpack2(wp[0][c], wv[0], wv[1]);
-                            unpack2(wp[1][c], wv[2], wv[3]);
-                            unpack2(wp[2][c], wv[4], wv[5]);
-                            wv[6] = ws[c];
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) unpack2(wp[q][c], wv[2 * q], wv[2 * q + 1]);
+                            if (ODD) wv[TI - 1] = ws[c];
 #pragma unroll
                             for (int t = 0; t < RW_TI; ++t) {
                                 accd[t] = fma((double)wv[t], h, accd[t]);          // exact products, fp64 sum
@@ -473,10 +475,14 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                     const float4 *Xq = reinterpret_cast<const float4 *>(smem + L.x_off + buf * RW_BUF_BYTES);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        unsigned long long ap[3][4];
+                        unsigned long long ap[NP][4];
                         float as[4];
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) { ap[0][b] = 0ull; ap[1][b] = 0ull; ap[2][b] = 0ull; as[b] = 0.f; }
+                        for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) ap[q][b] = 0ull;
+                            as[b] = 0.f;
+                        }
                         if (((done >> (4 * h)) & 0xfu) != 0xfu) {
 #pragma unroll
                             for (int c = 0; c < NC; ++c) {
@@ -485,19 +491,17 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                                 const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                                 for (int b = 0; b < 4; ++b) {
-                                    ffma2(ap[0][b], wp[0][c], xv[b]);
-                                    ffma2(ap[1][b], wp[1][c], xv[b]);
-                                    ffma2(ap[2][b], wp[2][c], xv[b]);
-                                    as[b] = fmaf(ws[c], xv[b], as[b]);
+#pragma unroll
+                                    for (int q = 0; q < NP; ++q) ffma2(ap[q][b], wp[q][c], xv[b]);
+                                    if (ODD) as[b] = fmaf(ws[c], xv[b], as[b]);
                                 }
                             }
                         }
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
-                            unpack2(ap[0][b], acc[0][4 * h + b], acc[1][4 * h + b]);
-                            unpack2(ap[1][b], acc[2][4 * h + b], acc[3][4 * h + b]);
-                            unpack2(ap[2][b], acc[4][4 * h + b], acc[5][4 * h + b]);
-                            acc[6][4 * h + b] = as[b];
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) unpack2(ap[q][b], acc[2 * q][4 * h + b], acc[2 * q + 1][4 * h + b]);
+                            if (ODD) acc[TI - 1][4 * h + b] = as[b];
                         }
                     }
                 }
@@ -517,7 +521,9 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                             h8[t][c] = keep + __shfl_xor_sync(full, send, 16);
                         }
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) h8[7][c] = 0.f;
+                    for (int t = RW_TI; t < 8; ++t)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) h8[t][c] = 0.f;
                     float h4[4][4], h2[2][4], h1[4];
 #pragma unroll
                     for (int t = 0; t < 4; ++t)
@@ -626,23 +632,26 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
 // host side
 // ------------------------------------------------------------------------------------
 typedef void (*RwKernel)(const RwArgs);
+static int rw_ti_for(int) { return 7; }                          // rows per warp of every instantiated shape
 static RwKernel pick_rw_kernel(int nc, int nw) {
     if (nw == 4) {
         switch (nc) {
-            case 2: return ssn_fp_regw_kernel<2, 4>;
-            case 4: return ssn_fp_regw_kernel<4, 4>;
-            case 7: return ssn_fp_regw_kernel<7, 4>;
-            case 10: return ssn_fp_regw_kernel<10, 4>;
-            case 14: return ssn_fp_regw_kernel<14, 4>;
+            case 2: return ssn_fp_regw_kernel<2, 4, 7>;
+            case 4: return ssn_fp_regw_kernel<4, 4, 7>;
+            case 7: return ssn_fp_regw_kernel<7, 4, 7>;
+            case 10: return ssn_fp_regw_kernel<10, 4, 7>;
+            case 14: return ssn_fp_regw_kernel<14, 4, 7>;
         }
         return nullptr;
     }
+    // (14-warp CTAs with 6 rows per warp -- 5-CTA clusters at 2N = 402 -- need ~200 live registers against a
+    //  budget of 144: ptxas spills 1.4 KB per thread, so that shape is not instantiated)
     switch (nc) {
-        case 2: return ssn_fp_regw_kernel<2, 8>;
-        case 4: return ssn_fp_regw_kernel<4, 8>;
-        case 7: return ssn_fp_regw_kernel<7, 8>;
-        case 10: return ssn_fp_regw_kernel<10, 8>;
-        case 14: return ssn_fp_regw_kernel<14, 8>;
+        case 2: return ssn_fp_regw_kernel<2, 8, 7>;
+        case 4: return ssn_fp_regw_kernel<4, 8, 7>;
+        case 7: return ssn_fp_regw_kernel<7, 8, 7>;
+        case 10: return ssn_fp_regw_kernel<10, 8, 7>;
+        case 14: return ssn_fp_regw_kernel<14, 8, 7>;
     }
     return nullptr;
 }
@@ -657,7 +666,7 @@ static int rw_nc_for(int dim) {
 struct RwPlan { RwKernel fn; int nc, nw, kpad, csize, rpc, smem, clusters, tab_nodes; };
 
 static int plan_regw_nw(const ssn_solver &sv, int n_sites, int nz, int nw, RwPlan *plan) {
-    const int dim = 2 * n_sites, rows = RW_TI * nw;
+    const int dim = 2 * n_sites, ti = rw_ti_for(nw), rows = ti * nw;
     plan->nw = nw;
     plan->nc = rw_nc_for(dim);
     if (!plan->nc) return 1;                                   // too large: caller falls back to the smem kernel
@@ -671,12 +680,13 @@ static int plan_regw_nw(const ssn_solver &sv, int n_sites, int nz, int nw, RwPla
     double v_end = (sv.io_type == SSN_IO_POWER || !(v0 < 160.0)) ? 160.0 : v0 + 1.0;
     if (!(v_end > 2.0)) v_end = 2.0;
     plan->tab_nodes = (int)((v_end - TAB_V_MIN) * TAB_PER_UNIT) + 2;
-    plan->smem = rw_smem_layout(plan->kpad, n_sites, plan->tab_nodes, 32 * nw).total;
+    plan->smem = rw_smem_layout(plan->kpad, n_sites, plan->tab_nodes, 32 * nw, ti).total;
     int dev = 0, limit = 0;
     SSN_CUDA(cudaGetDevice(&dev));
     SSN_CUDA(cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     if (plan->smem > limit) return 1;
     plan->fn = pick_rw_kernel(plan->nc, nw);
+    if (!plan->fn) return 1;
     SSN_CUDA(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem));
     if (plan->csize > 8) SSN_CUDA(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -702,7 +712,7 @@ static int plan_regw_nw(const ssn_solver &sv, int n_sites, int nz, int nw, RwPla
 static int plan_regw(const ssn_solver &sv, int n_sites, int nz, RwPlan *plan) {
     const char *force = getenv("SSN_REGW_WARPS");
     const int first = force ? atoi(force) : 8;
-    int rc = plan_regw_nw(sv, n_sites, nz, first == 8 ? 8 : 4, plan);
+    int rc = plan_regw_nw(sv, n_sites, nz, first == 4 ? 4 : 8, plan);
     if (rc == 1 && !force) rc = plan_regw_nw(sv, n_sites, nz, 4, plan);
     return rc;
 }
