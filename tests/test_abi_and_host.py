@@ -148,3 +148,32 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(base, f)).read()
                 assert 'ssn_oracle' not in text and 'oracle/' not in text, os.path.join(base, f)
+
+
+def test_hetero_input_and_critic_loss_on_cpu(built_library):
+    """Host-side torch helpers of the widened rows (no GPU needed): heterogeneous stimulus
+    (tc_gan/networks/ssn.py:645-727) and the WGAN-GP critic loss (networks/wgan.py:194-215)."""
+    import torch
+    from tc_gan_b200 import gan, torch_ops
+    ext = torch.arange(12., dtype=torch.float64).reshape(2, 6)          # nb=2, 2N=6
+    zs = torch.tensor([[1., -1., 1., -1., 1., -1.], [0.5, 0.5, 0.5, -0.5, -0.5, -0.5]], dtype=torch.float64)
+    V = torch.tensor([0.2, 0.4], dtype=torch.float64, requires_grad=True)
+    out = torch_ops.hetero_input(ext, zs, V)
+    assert out.shape == (2, 2, 6)
+    want = (1 + torch.tensor([0.2] * 3 + [0.4] * 3, dtype=torch.float64) * zs[:, None, :]) * ext[None]
+    assert torch.allclose(out, want)
+    out.sum().backward()
+    assert torch.allclose(V.grad, torch.stack([(zs[:, None, :3] * ext[None, :, :3]).sum(),
+                                               (zs[:, None, 3:] * ext[None, :, 3:]).sum()]))
+    deg = torch_ops.hetero_input(ext, zs, torch.tensor(0.3, dtype=torch.float64))
+    assert torch.allclose(deg, (1 + 0.3 * zs[:, None, :]) * ext[None])
+    torch.manual_seed(0)
+    critic = gan.Critic(6, layers=(8,), layer_norm=True).double()
+    fake, real = torch.randn(5, 6, dtype=torch.float64), torch.randn(7, 6, dtype=torch.float64)
+    loss, acc = gan.critic_loss(critic, fake, real, lipschitz_cost=10.0)
+    assert loss.requires_grad and not acc.requires_grad and torch.isfinite(loss)
+    assert abs(float(acc) - float(critic(fake).mean() - critic(real).mean())) < 1e-12
+    loss0, _ = gan.critic_loss(critic, fake, real, lipschitz_cost=0.0)
+    assert abs(float(loss0) - float(acc)) < 1e-12                     # penalty-free loss is the accuracy
+    with pytest.raises(ValueError):
+        gan.SSNWassersteinGAN(np.zeros((4, 8), np.float32), mode='nope', device='cpu')
