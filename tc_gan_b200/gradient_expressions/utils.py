@@ -16,9 +16,9 @@ def sample_sites_from_stim_space(stim_locs, N):
     >>> sample_sites_from_stim_space([0, 0.5, 1], 101)
     [50, 75, 100]
     """
-    stim_locs = np.asarray(stim_locs)
-    assert all(stim_locs >= -1)
-    assert all(stim_locs <= 1)
+    stim_locs = np.asarray(stim_locs, dtype=float)
+    if stim_locs.size and (stim_locs.min() < -1 or stim_locs.max() > 1):
+        raise AssertionError('stimulus-space locations must lie in [-1, 1]')
     sample_sites = sample_sites_from_stim_space_impl(stim_locs, N)
     if len(sample_sites) != len(set(sample_sites)):
         raise ValueError(
@@ -33,8 +33,10 @@ def sample_sites_from_stim_space(stim_locs, N):
 def subsample_neurons(rate_vector, sample_sites, track_offset_identity=False,
                       include_inhibitory_neurons=False, N=None, NZ=None, NB=None):
     """
-    (NZ, NB, 2N) rates -> (NZ * n_sites, NB), or (NZ, NB * n_sites) when
-    track_offset_identity.  Works on numpy arrays and torch tensors.
+    Rates (NZ, NB, 2N) -> what the critic sees.  Probed neurons are `sample_sites` (excitatory
+    indices; with include_inhibitory_neurons also their inhibitory partners at +N).  The probes of
+    one network either stay together, (NZ, NB * n_probes) when track_offset_identity, or become
+    separate samples, (NZ * n_probes, NB).  numpy arrays and torch tensors.
 
     >>> r = np.tile(np.arange(14), (5, 2, 1))
     >>> subsample_neurons(r, [2, 3, 4]).shape
@@ -42,19 +44,17 @@ def subsample_neurons(rate_vector, sample_sites, track_offset_identity=False,
     >>> subsample_neurons(r, [2, 3, 4], True)[0].tolist()
     [2, 3, 4, 2, 3, 4]
     """
-    NZ_, NB_, TN_ = rate_vector.shape
-    NZ = NZ_ if NZ is None else NZ
-    NB = NB_ if NB is None else NB
-    N = TN_ // 2 if N is None else N
-    assert (NZ_, NB_, TN_) == (NZ, NB, 2 * N)
-    assert 0 <= min(sample_sites)
-    assert max(sample_sites) < N
-    sample_sites = list(sample_sites)
+    nz, nb, width = rate_vector.shape
+    n_sites = width // 2 if N is None else N
+    if (NZ is not None and NZ != nz) or (NB is not None and NB != nb) or width != 2 * n_sites:
+        raise AssertionError('rate_vector must have shape (NZ, NB, 2N)')
+    probes = [int(p) for p in sample_sites]
+    if not probes or min(probes) < 0 or max(probes) >= n_sites:
+        raise AssertionError('sample_sites must lie in [0, N)')
     if include_inhibitory_neurons:
-        sample_sites = sample_sites + [s + N for s in sample_sites]
-    subsample = rate_vector[:, :, sample_sites]
+        probes += [p + n_sites for p in probes]
+    picked = rate_vector[:, :, probes]                              # (NZ, NB, n_probes)
     if track_offset_identity:
-        return subsample.reshape((NZ, -1))
-    if isinstance(subsample, np.ndarray):
-        return subsample.swapaxes(1, 2).reshape((-1, NB))
-    return subsample.transpose(1, 2).reshape((-1, NB))
+        return picked.reshape((nz, nb * len(probes)))
+    moved = picked.swapaxes(1, 2) if isinstance(picked, np.ndarray) else picked.transpose(1, 2)
+    return moved.reshape((nz * len(probes), nb))

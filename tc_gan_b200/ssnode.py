@@ -26,51 +26,49 @@ from .clib import libssnode, double_ptr
 from .gradient_expressions.utils import subsample_neurons
 
 
-DEFAULT_PARAMS = dict(
-    N=102,
-    J=np.array([[.0957, .0638], [.1197, .0479]]),
-    D=np.array([[.7660, .5106], [.9575, .3830]]),
-    S=np.array([[.6667, .2], [1.333, .2]]) / 8,
-    bandwidths=[0, 0.0625, 0.125, 0.1875, 0.25, 0.5, 0.75, 1],
-    smoothness=0.25/8,
-    contrast=[20],
-    offset=[0],
-    io_type='asym_tanh',
-    k=0.01,
-    n=2.2,
-    rate_soft_bound=200, rate_hard_bound=1000,
-    tau=(0.01589, 0.002),
-)
+_J0 = np.array([[.0957, .0638], [.1197, .0479]])
+_D0 = np.array([[.7660, .5106], [.9575, .3830]])
+_S0 = np.array([[.6667, .2], [1.333, .2]]) / 8
+
+# Same keys and values as tc_gan.ssnode.DEFAULT_PARAMS (ssnode.py:27-41).
+DEFAULT_PARAMS = {
+    'N': 102, 'J': _J0, 'D': _D0, 'S': _S0,
+    'bandwidths': [0, 0.0625, 0.125, 0.1875, 0.25, 0.5, 0.75, 1],
+    'smoothness': 0.25 / 8, 'contrast': [20], 'offset': [0],
+    'io_type': 'asym_tanh', 'k': 0.01, 'n': 2.2,
+    'rate_soft_bound': 200, 'rate_hard_bound': 1000,
+    'tau': (0.01589, 0.002),
+}
+
+_IO_TYPES = ('asym_linear', 'asym_tanh', 'asym_power')
+_MESSAGES = {0: "Converged", 1: "SSN Convergence Failed", 2: "Reached to rate_stop_at"}
 
 
 def new_JDS():
-    """More stable generator parameters (networks/fixed_time_sampler.py:12-23)."""
-    D_new = DEFAULT_PARAMS['D'] / 2
-    J_new = DEFAULT_PARAMS['J'] + DEFAULT_PARAMS['D'] / 2 - D_new / 2
-    return dict(J=J_new, D=D_new, S=DEFAULT_PARAMS['S'].copy())
+    """More stable generator parameters (networks/fixed_time_sampler.py:12-23): D/2, J + D/4."""
+    return dict(J=_J0 + _D0 / 4, D=_D0 / 2, S=_S0.copy())
 
 
 class FixedPointResult(object):
+    """Outcome of one solve: state `x`, reference error code `error`, `message`, `success`;
+    `iterations` is filled by the batched path (the reference does not report it)."""
 
-    message = None
+    __slots__ = ('x', 'error', 'message', 'iterations')
 
     def __init__(self, x, error, iterations=None):
-        self.x = x
-        self.error = error
-        self.iterations = iterations
+        self.x, self.error, self.iterations, self.message = x, error, iterations, None
 
-    @property
-    def success(self):
-        return self.error == 0
+    success = property(lambda self: self.error == 0)
 
     def to_exception(self):
         return FixedPointError(self.message, self)
 
 
 class FixedPointError(Exception):
+    """Raised with ``check=True``; carries the failed `FixedPointResult` as ``.result``."""
 
     def __init__(self, message, result):
-        super(FixedPointError, self).__init__(message)
+        Exception.__init__(self, message)
         self.result = result
 
 
@@ -79,14 +77,13 @@ def take(n, iterable):
 
 
 def make_neu_vec(N, E, I):
-    return np.array([E] * N + [I] * N)
+    """2N-vector from population-level values."""
+    return np.repeat(np.array([E, I]), N)
 
 
 def any_to_neu_vec(N, vec):
     vec = np.asarray(vec)
-    if len(vec) == 2:
-        vec = make_neu_vec(N, *vec)
-    return vec
+    return make_neu_vec(N, *vec) if len(vec) == 2 else vec
 
 
 def thlin(x):
@@ -94,10 +91,11 @@ def thlin(x):
 
 
 def rate_to_volt(rate, k, n):
-    return (rate / k)**(1 / n)
+    return (rate / k) ** (1 / n)
 
 
 def _xp(a):
+    """numpy, or torch for torch tensors (the reference dispatches numpy / Theano the same way)."""
     try:
         import torch
         if isinstance(a, torch.Tensor):
@@ -107,24 +105,25 @@ def _xp(a):
     return np
 
 
-def io_alin(v, volt_max, k, n):
-    xp = _xp(v)
-    vc = xp.clip(v, 0, volt_max)
-    rate = k * (vc**n)
-    linear = k * (volt_max**(n-1)) * n * (v - volt_max)
-    return xp.where(v <= volt_max, rate, rate + linear)
-
-
 def io_power(v, k, n):
-    return k * (thlin(v)**n)
+    return k * thlin(v) ** n
+
+
+def io_alin(v, volt_max, k, n):
+    """Power law up to volt_max, then its tangent line (ssnode.py:129-134)."""
+    xp = _xp(v)
+    below = k * xp.clip(v, 0, volt_max) ** n
+    slope = k * n * volt_max ** (n - 1)
+    return xp.where(v <= volt_max, below, below + slope * (v - volt_max))
 
 
 def io_atanh(v, r0, r1, v0, k, n):
+    """Power law up to v0 (rate r0), then a tanh saturating at r1 (ssnode.py:142-149)."""
     xp = _xp(v)
-    v_pow = xp.clip(v, 0, v0)
-    r_pow = k * (v_pow**n)
-    r_tanh = r0 + (r1 - r0) * xp.tanh(n * r0 / (r1 - r0) * (v - v0) / v0)
-    return xp.where(v <= v0, r_pow, r_tanh)
+    below = k * xp.clip(v, 0, v0) ** n
+    span = r1 - r0
+    above = r0 + span * xp.tanh(n * r0 / span * (v - v0) / v0)
+    return xp.where(v <= v0, below, above)
 
 
 def make_io_fun(k, n,
@@ -133,21 +132,18 @@ def make_io_fun(k, n,
                 io_type=DEFAULT_PARAMS['io_type']):
     """Elementwise transfer function on numpy arrays / torch tensors (ssnode.py:276-292)."""
     v0 = rate_to_volt(rate_soft_bound, k, n)
-    if io_type == 'asym_linear':
-        def io_fun(v):
-            return io_alin(v, v0, k, n)
-    elif io_type == 'asym_tanh':
-        def io_fun(v):
-            return io_atanh(v, rate_soft_bound, rate_hard_bound, v0, k, n)
-    elif io_type == 'asym_power':
-        def io_fun(v):
-            return io_power(v, k, n)
-    else:
+    table = {
+        'asym_linear': lambda v: io_alin(v, v0, k, n),
+        'asym_tanh': lambda v: io_atanh(v, rate_soft_bound, rate_hard_bound, v0, k, n),
+        'asym_power': lambda v: io_power(v, k, n),
+    }
+    if io_type not in table:
         raise ValueError("Unknown I/O type: {}".format(io_type))
-    return io_fun
+    return table[io_type]
 
 
 def solve_dynamics(*args, **kwds):
+    """`fixed_point(...).x`, printing the message of a failed solve (ssnode.py:152-156)."""
     sol = fixed_point(*args, **kwds)
     if not sol.success:
         print(sol.message)
@@ -155,23 +151,17 @@ def solve_dynamics(*args, **kwds):
 
 
 def _set_message(sol):
-    """Error code -> message, exactly as ssnode.py:256-270."""
-    error = sol.error
-    if error == 0:
-        if np.isfinite(sol.x).all():
-            sol.message = "Converged"
-        else:
-            sol.error = 1
-            sol.message = "Converged to non-finite value"
-    elif error == 1:
-        sol.message = "SSN Convergence Failed"
-    elif error == 2:
-        sol.message = "Reached to rate_stop_at"
-    elif error > 900:
+    """Error code -> message exactly as ssnode.py:256-270 (a converged but non-finite state is error 1)."""
+    code = sol.error
+    if code == 0 and not np.isfinite(sol.x).all():
+        sol.error, sol.message = 1, "Converged to non-finite value"
+    elif code in _MESSAGES:
+        sol.message = _MESSAGES[code]
+    elif code > 900:
         sol.message = "CUDA error {}: {}".format(
-            error - 1000, libssnode.ssn_last_error().decode('utf-8', 'replace'))
+            code - 1000, libssnode.ssn_last_error().decode('utf-8', 'replace'))
     else:
-        sol.message = "Unknown error: code={}".format(error)
+        sol.message = "Unknown error: code={}".format(code)
     return sol
 
 
@@ -185,48 +175,36 @@ def fixed_point(
     """
     Solve the SSN ODE for one (W, ext) until it reaches a fixed point.
 
-    Same signature and result as tc_gan.ssnode.fixed_point (ssnode.py:159-273);
-    the Euler loop runs on the GPU in float64 through the reference C ABI
-    ``solve_dynamics_{io_type}_{solver}``.  A failure of the GPU call itself
-    raises `clib.SSNLibraryError` (there is no CPU fallback).
+    Same signature and result as tc_gan.ssnode.fixed_point (ssnode.py:159-273): `W` is
+    (2N, 2N), `ext` and `r0` (2N,), the result a `FixedPointResult`.  The Euler loop runs on
+    the GPU in float64 behind the reference's own C symbol ``solve_dynamics_{io_type}_{solver}``.
+    Unlike the reference, non-contiguous inputs are honoured (it passes the raw buffer).  A
+    failure of the GPU call itself raises `clib.SSNLibraryError`: there is no CPU fallback.
     """
-    if io_type not in ('asym_linear', 'asym_tanh', 'asym_power'):
+    if io_type not in _IO_TYPES:
         raise ValueError("Unknown I/O type: {}".format(io_type))
-    if solver not in ('euler',):
+    if solver != 'euler':
         raise ValueError("Unknown solver: {}".format(solver))
 
-    W = np.ascontiguousarray(W, dtype='double')
-    N = W.shape[0] // 2
-    ext = np.ascontiguousarray(ext, dtype='double')
-    if r0 is None:
-        r0 = np.zeros(2 * N, dtype='double')
-    else:
-        r0 = np.array(r0, dtype='double')  # copied, as it will be modified
-    r1 = np.empty_like(r0)
-    tau_E, tau_I = tau
+    Wc = np.ascontiguousarray(W, dtype=np.float64)
+    ec = np.ascontiguousarray(ext, dtype=np.float64)
+    dim = Wc.shape[0]
+    if Wc.ndim != 2 or Wc.shape != (dim, dim) or dim % 2 or ec.shape != (dim,):
+        raise AssertionError('W must be (2N, 2N) and ext (2N,)')
+    state = np.zeros(dim) if r0 is None else np.array(r0, dtype=np.float64)   # copy: overwritten by the solver
+    if state.shape != (dim,):
+        raise AssertionError('r0 must be (2N,)')
+    scratch = np.empty(dim)
+    # power / linear transfer functions have no saturation: the hard bound is the stop criterion
+    bound = rate_hard_bound if io_type == 'asym_tanh' else rate_stop_at
 
-    assert 2 * N == W.shape[0] == W.shape[1]
-    assert W.ndim == 2
-    assert (2 * N,) == r0.shape == ext.shape
-
-    if io_type in ('asym_power', 'asym_linear'):
-        rate_hard_bound = rate_stop_at
-
-    error = getattr(libssnode,
-                    'solve_dynamics_{}_{}'.format(io_type, solver))(
-        N,
-        W.ctypes.data_as(double_ptr),
-        ext.ctypes.data_as(double_ptr),
-        float(k), float(n),
-        r0.ctypes.data_as(double_ptr),
-        r1.ctypes.data_as(double_ptr),
-        tau_E, tau_I,
-        dt, max_iter, atol,
-        rate_soft_bound, rate_hard_bound,
-    )
-    if error > 900:
-        clib.check_call(error, 'solve_dynamics_{}_{}'.format(io_type, solver))
-    sol = _set_message(FixedPointResult(r0, error))
+    symbol = getattr(libssnode, 'solve_dynamics_{}_{}'.format(io_type, solver))
+    code = symbol(dim // 2, Wc.ctypes.data_as(double_ptr), ec.ctypes.data_as(double_ptr),
+                  float(k), float(n), state.ctypes.data_as(double_ptr), scratch.ctypes.data_as(double_ptr),
+                  tau[0], tau[1], dt, max_iter, atol, rate_soft_bound, bound)
+    if code > 900:
+        clib.check_call(code, symbol.__name__)
+    sol = _set_message(FixedPointResult(state, code))
     if check and not sol.success:
         raise sol.to_exception()
     return sol
