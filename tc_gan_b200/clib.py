@@ -29,7 +29,8 @@ double_ptr = ctypes.POINTER(ctypes.c_double)
 float_ptr = ctypes.POINTER(ctypes.c_float)
 int_ptr = ctypes.POINTER(ctypes.c_int)
 
-libssnode = load_library('libssnode')
+# SSN_LIBNAME selects an instrumented build of the same library (`make -C tc_gan_b200/csrc prof`)
+libssnode = load_library(os.environ.get('SSN_LIBNAME', 'libssnode'))
 
 # ---- reference ABI (tc_gan/clib.py:16-33) ---------------------------------------
 for fun in [libssnode.solve_dynamics_asym_power_euler,

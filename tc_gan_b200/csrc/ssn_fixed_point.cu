@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <mutex>
 #include "ssn_cluster_core.cuh"
+#include <cstring>
 #include "ssn_launch.h"
 
 namespace ssn {
@@ -424,9 +425,12 @@ static int plan_fixed_point(int n_sites, int nz, FpLaunchPlan *plan) {
 }
 
 int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters) {
-    if (!getenv("SSN_FORCE_SMEM_KERNEL")) {
+    const char *k1 = getenv("SSN_K1");
+    const int first = getenv("SSN_FORCE_SMEM_KERNEL") ? 2 : !k1 ? 0 : !strcmp(k1, "regw") ? 1 : !strcmp(k1, "smem") ? 2 : 0;
+    if (first <= 1) {
         ssn_solver sv = {};
         sv.io_type = SSN_IO_TANH; sv.k = 0.01; sv.n = 2.2; sv.rate_soft_bound = 200; sv.rate_hard_bound = 1000;
+        if (first <= 0 && ws_occupancy(sv, n_sites, cluster_size, resident_clusters) == 0) return 0;
         if (regw_occupancy(sv, n_sites, cluster_size, resident_clusters) == 0) return 0;
     }
     FpLaunchPlan plan;
@@ -443,9 +447,17 @@ int launch_fixed_point_f32(const ssn_solver &sv, int nz, int nb, int n_sites, in
                            float *R, int *status, int *iters, int *counter, cudaStream_t stream) {
     if (nz <= 0 || nb <= 0) return 0;
     const int n_solves_all = nz * nb;
-    int rc = getenv("SSN_FORCE_SMEM_KERNEL") ? 1 : launch_fixed_point_regw(sv, nz, nb, n_sites, w_kind, w, jds, ext,
-                                                                          ext_per_network, r_init, R, status, iters,
-                                                                          counter, stream);
+    // Kernel choice: the warp-specialised register kernel, else the lockstep register kernel, else the
+    // shared-memory kernel (shapes out of range return 1).  SSN_K1 = ws | regw | smem forces a starting point.
+    const char *k1 = getenv("SSN_K1");
+    const int first = getenv("SSN_FORCE_SMEM_KERNEL") ? 2 : !k1 ? 0 : !strcmp(k1, "regw") ? 1 : !strcmp(k1, "smem") ? 2 : 0;
+    int rc = 1;
+    if (first <= 0)
+        rc = launch_fixed_point_ws(sv, nz, nb, n_sites, w_kind, w, jds, ext, ext_per_network, r_init, R, status, iters,
+                                   counter, stream);
+    if (rc == 1 && first <= 1)
+        rc = launch_fixed_point_regw(sv, nz, nb, n_sites, w_kind, w, jds, ext, ext_per_network, r_init, R, status,
+                                     iters, counter, stream);
     if (rc == 0) {
         ssn_status_fixup_kernel<<<(n_solves_all * 32 + 255) / 256, 256, 0, stream>>>(R, status, n_solves_all, 2 * n_sites);
         SSN_CUDA(cudaGetLastError());

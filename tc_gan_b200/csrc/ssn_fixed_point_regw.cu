@@ -24,7 +24,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
-#include "ssn_cluster_core.cuh"
+#include "ssn_regw_common.cuh"
 #include "ssn_launch.h"
 
 namespace ssn {
@@ -38,29 +38,6 @@ constexpr int RW_XE = 4;                               // stimuli refreshed per 
 // (TI = rows per warp: 7 -> 15 slots, 240 B per block; the slot after the last block is always zero)
 __host__ __device__ constexpr int rw_blk_slots(int ti) { return 2 * ti + 1; }
 __host__ __device__ constexpr int rw_buf_bytes(int ti) { return (RW_BLOCKS * rw_blk_slots(ti) + 1) * 16; }
-constexpr int TAB_PER_UNIT = 8;                        // table nodes per unit of v
-constexpr double TAB_V_MIN = 1.0;
-
-struct RwArgs {
-    int nz, nb, n_sites, dim, kpad, csize, rpc;
-    int w_kind;
-    const float *w;
-    WeightConst wc;
-    const float *ext;
-    long long ext_stride_z;
-    const float *r_init;
-    float *R;
-    int *status, *iters;
-    int *work_counter;
-    IoConst<double> io;
-    IoConst<float> iof;
-    double eps_E, eps_I, atol, r_hard, t_first;        // t_first: first refresh threshold on |dr|
-    int max_iter, check_hard, tab_nodes;
-    float tab_end;                                     // v at the last table node
-    int dbg;                                           // development switches (SSN_DBG), 0 in production
-    long long *dbg_out;                                // phase cycle counters when dbg & 4
-};
-
 struct RwSmem {
     int x_off, xe_off, tab_off, gtab_off, state_off, misc_off, total;
 };
@@ -73,114 +50,17 @@ struct RwMisc {
     unsigned pdelta[RW_MAXC];
     int next_net;
 };
-__host__ __device__ inline RwSmem rw_smem_layout(int kpad, int n_sites, int tab_nodes, int nt, int ti) {
+__host__ __device__ inline RwSmem rw_smem_layout(int kpad, int n_sites, int tab_bytes, int nt, int ti) {
     RwSmem L;
     int o = 0;
     L.x_off = o;    o += 2 * rw_buf_bytes(ti);         // [buf][source CTA][warp] blocks + a zero slot
     L.xe_off = o;   o += 2 * RW_XE * kpad * 4;         // exact-pass columns: hi[4][kpad], lo[4][kpad]
-    L.tab_off = o;  o += tab_nodes * 32;               // cubic table of f: 4 doubles per node
+    L.tab_off = o;  o += tab_bytes;                       // Taylor tables of f
     L.gtab_off = o; o += ((4 * n_sites * 4 + 15) / 16) * 16;
     L.state_off = o; o += rw_state_bytes(nt);
     L.misc_off = o; o += 1024;
     L.total = o;
     return L;
-}
-
-// ---- mbarrier / st.async helpers ---------------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done = 0;
-    while (!done)
-        asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;"
-            " selp.u32 %0, 1, 0, p; }"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void st_async_v4(unsigned addr, float4 v, unsigned bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                 ::"r"(addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
-                   "r"(__float_as_uint(v.w)), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void st_async_v2(unsigned addr, float a, float b, unsigned bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
-                 ::"r"(addr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_release(unsigned bar) {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_to_peer(unsigned dst_remote, unsigned src_local, unsigned bytes, unsigned bar_remote) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_remote), "r"(src_local), "r"(bytes), "r"(bar_remote) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void st_async_u32(unsigned addr, unsigned v, unsigned bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-                 ::"r"(addr), "r"(v), "r"(bar) : "memory");
-}
-
-// packed FP32 pairs (FFMA2): a register pair holds rows (2p, 2p+1) of the W tile / of the accumulators, so one
-// fma.rn.f32x2 with the broadcast x does two FMAs and its operands can never collide on a register bank
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long v;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
-    return v;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long long w, float x) {
-    unsigned long long xx;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(w), "l"(xx));
-}
-
-// f(v) in float64.  Common case (1 <= v within the table, power-law branch): cubic expansion around the
-// nearest node -- index from an FP32 estimate, offset and Horner in FP64, no branches.  v < 1: accurate
-// enough in FP32 (|f| < k, absolute error ~1e-8 k).  Above the soft bound / beyond the table: closed form
-// behind a (rare, warp-divergent) branch.
-__device__ __forceinline__ double io_eval_table(const RwArgs &a, const double *tab, double v) {
-    const float vf = (float)v;
-    int i = __float2int_rn((vf - (float)TAB_V_MIN) * (float)TAB_PER_UNIT);
-    i = max(0, min(i, a.tab_nodes - 1));
-    const double s = fma(v, (double)TAB_PER_UNIT, -TAB_V_MIN * TAB_PER_UNIT) - (double)i;
-    const double2 c01 = *reinterpret_cast<const double2 *>(tab + 4 * i);
-    const double2 c23 = *reinterpret_cast<const double2 *>(tab + 4 * i + 2);
-    double f = fma(s, fma(s, fma(s, c23.y, c23.x), c01.y), c01.x);
-    const float flow = a.iof.k * exp2f(a.iof.n * __log2f(fmaxf(vf, 1e-30f)));
-    f = vf < (float)TAB_V_MIN ? (double)flow : f;
-    f = v > 0.0 ? f : (v != v ? v : 0.0);
-    const bool upper = a.io.io_type != SSN_IO_POWER && v > a.io.v0;
-    if (upper || vf >= a.tab_end) {                       // rare: saturating / diverging neurons
-        if (upper)
-            f = a.io.io_type == SSN_IO_LINEAR ? fma(a.io.lin_slope, v - a.io.v0, a.io.r_soft)
-                                              : a.io.r_soft + a.io.span * tanh(a.io.tanh_scale * (v - a.io.v0));
-        else
-            f = a.io.k * pow(v, a.io.n);
-    }
-    return f;
-}
-
-// Common path of io_eval_table without the rare branch; `rare` reports whether the closed form is needed.
-__device__ __forceinline__ double io_eval_common(const RwArgs &a, const double *tab, double v, bool &rare) {
-    const float vf = (float)v;
-    int i = __float2int_rn((vf - (float)TAB_V_MIN) * (float)TAB_PER_UNIT);
-    i = max(0, min(i, a.tab_nodes - 1));
-    const double s = fma(v, (double)TAB_PER_UNIT, -TAB_V_MIN * TAB_PER_UNIT) - (double)i;
-    const double2 c01 = *reinterpret_cast<const double2 *>(tab + 4 * i);
-    const double2 c23 = *reinterpret_cast<const double2 *>(tab + 4 * i + 2);
-    double f = fma(s, fma(s, fma(s, c23.y, c23.x), c01.y), c01.x);
-    const float flow = a.iof.k * exp2f(a.iof.n * __log2f(fmaxf(vf, 1e-30f)));
-    f = vf < (float)TAB_V_MIN ? (double)flow : f;
-    f = v > 0.0 ? f : (v != v ? v : 0.0);
-    rare = (a.io.io_type != SSN_IO_POWER && v > a.io.v0) || vf >= a.tab_end;
-    return f;
 }
 
 template <int NC, int NW, int TI>
@@ -194,7 +74,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int csize = a.csize, dim = a.dim, kpad = a.kpad, rpc = a.rpc, N = a.n_sites;
-    const RwSmem L = rw_smem_layout(kpad, N, a.tab_nodes, RW_THREADS, TI);
+    const RwSmem L = rw_smem_layout(kpad, N, rw_table_bytes(a.tab_nodes, a.tab2_nodes), RW_THREADS, TI);
     float *Xf = reinterpret_cast<float *>(smem + L.x_off);
     float *xe = reinterpret_cast<float *>(smem + L.xe_off);
     double *tab = reinterpret_cast<double *>(smem + L.tab_off);
@@ -242,14 +122,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
     for (int i = tid; i < 2 * RW_BUF_BYTES / 4; i += RW_THREADS) Xf[i] = 0.f;
     for (int i = tid; i < 2 * RW_XE * kpad; i += RW_THREADS) xe[i] = 0.f;
     if (a.w_kind == SSN_W_FROM_Z) build_profile_table(a.wc, N, gtab, tid, RW_THREADS);
-    for (int i = tid; i < a.tab_nodes; i += RW_THREADS) {           // cubic table of k v^n
-        const double v = TAB_V_MIN + (double)i / TAB_PER_UNIT, h = 1.0 / TAB_PER_UNIT;
-        const double n = a.io.n, p3 = pow(v, n - 3.0);
-        tab[4 * i + 0] = a.io.k * p3 * v * v * v;
-        tab[4 * i + 1] = a.io.k * n * p3 * v * v * h;
-        tab[4 * i + 2] = a.io.k * n * (n - 1.0) * p3 * v * h * h * 0.5;
-        tab[4 * i + 3] = a.io.k * n * (n - 1.0) * (n - 2.0) * p3 * h * h * h / 6.0;
-    }
+    build_io_tables(a, tab, tid, RW_THREADS);
     cluster.sync();
 
     unsigned ph[2] = {0u, 0u}, xph = 0u;
@@ -573,8 +446,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 2 : 1) ssn_fp_regw_kernel(c
                         fv[i] = io_eval_common(a, tab, vv[i], rare[i]);
                     }
                     if (rare[0] | rare[1]) {                                   // saturating / diverging neurons only
-                        if (rare[0]) fv[0] = io_eval_table(a, tab, vv[0]);
-                        if (rare[1]) fv[1] = io_eval_table(a, tab, vv[1]);
+                        if (rare[0]) fv[0] = io_eval_exact(a, vv[0]);
+                        if (rare[1]) fv[1] = io_eval_exact(a, vv[1]);
                     }
                     if (a.dbg & 2) { fv[0] = vv[0]; fv[1] = vv[1]; }
 #pragma unroll
@@ -675,12 +548,8 @@ static int plan_regw_nw(const ssn_solver &sv, int n_sites, int nz, int nw, RwPla
     if (plan->csize > (nw == 4 ? RW_MAXC : MAX_CLUSTER) || plan->csize * nw > RW_BLOCKS) return 1;
     plan->rpc = (dim + plan->csize - 1) / plan->csize;
     if (plan->rpc * (plan->csize - 1) >= dim) return 1;
-    // table of k v^n on [1, min(v0, 160)] (power type: to 160, beyond it the closed form is used)
-    const double v0 = pow(sv.rate_soft_bound / sv.k, 1.0 / sv.n);
-    double v_end = (sv.io_type == SSN_IO_POWER || !(v0 < 160.0)) ? 160.0 : v0 + 1.0;
-    if (!(v_end > 2.0)) v_end = 2.0;
-    plan->tab_nodes = (int)((v_end - TAB_V_MIN) * TAB_PER_UNIT) + 2;
-    plan->smem = rw_smem_layout(plan->kpad, n_sites, plan->tab_nodes, 32 * nw, ti).total;
+    plan->tab_nodes = rw_table_nodes(sv);
+    plan->smem = rw_smem_layout(plan->kpad, n_sites, rw_table_bytes(plan->tab_nodes, rw_table2_nodes(sv)), 32 * nw, ti).total;
     int dev = 0, limit = 0;
     SSN_CUDA(cudaGetDevice(&dev));
     SSN_CUDA(cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -744,18 +613,7 @@ int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, i
     }
     a.ext = ext; a.ext_stride_z = ext_per_network ? (long long)nb * 2 * n_sites : 0;
     a.r_init = r_init; a.R = R; a.status = status; a.iters = iters; a.work_counter = counter;
-    a.io = make_io_const<double>(sv.io_type, sv.k, sv.n, sv.rate_soft_bound, sv.rate_hard_bound);
-    a.iof = make_io_const<float>(sv.io_type, sv.k, sv.n, sv.rate_soft_bound, sv.rate_hard_bound);
-    a.eps_E = sv.dt / sv.tau_E; a.eps_I = sv.dt / sv.tau_I;
-    a.atol = sv.atol; a.r_hard = sv.rate_hard_bound;
-    a.max_iter = sv.max_iter; a.check_hard = sv.io_type != SSN_IO_TANH;
-    a.tab_nodes = plan.tab_nodes;
-    a.tab_end = (float)(TAB_V_MIN + (double)(plan.tab_nodes - 1) / TAB_PER_UNIT - 0.5 / TAB_PER_UNIT);
-    a.dbg = getenv("SSN_DBG") ? atoi(getenv("SSN_DBG")) : 0;
-    // refresh ladder: thresholds atol * 64^j, starting at the largest one below 0.1
-    double t = sv.atol > 0 ? sv.atol : 1e-300;
-    while (t * 64.0 < 0.1) t *= 64.0;
-    a.t_first = t > sv.atol ? t : 0.0;
+    rw_fill_solver_args(a, sv, plan.tab_nodes);
 
     SSN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
     cudaLaunchConfig_t cfg = {};

@@ -15,6 +15,11 @@ int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters
 int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
                             const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
                             float *R, int *status, int *iters, int *counter, cudaStream_t stream);
+// warp-specialised register-resident-W kernel (default); returns 1 when the shape is outside its range
+int launch_fixed_point_ws(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
+                          const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
+                          float *R, int *status, int *iters, int *counter, cudaStream_t stream);
+int ws_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *resident_clusters);
 int regw_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *resident_clusters);
 
 int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,

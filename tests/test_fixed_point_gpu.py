@@ -251,6 +251,23 @@ def test_tight_atol_on_the_fast_path(ssn, oracle):
     assert np.abs(its - it_o).max() <= 2
 
 
+def test_lockstep_register_kernel(ssn, oracle):
+    """The register-resident kernel without warp specialisation (SSN_K1=regw; the path taken when the
+    warp-specialised kernel cannot be planned) meets the same bar as the default kernel."""
+    os.environ['SSN_K1'] = 'regw'
+    try:
+        for n_sites, nz, nb in ((33, 3, 8), (101, 2, 9), (201, 2, 8)):
+            bw = np.linspace(0, 1, nb)
+            _, W, exts = seeded_problem(oracle, n_sites, nz, seed=20 + n_sites, bandwidths=bw)
+            Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+            R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2)
+            np.testing.assert_array_equal(err, st_o)
+            np.testing.assert_allclose(R, Ro, rtol=RTOL, atol=ATOL)
+            check_sweeps(its, it_o)
+    finally:
+        del os.environ['SSN_K1']
+
+
 def test_shared_memory_fallback_kernel(ssn, oracle):
     """The cluster/DSMEM kernel that keeps W in shared memory (used beyond 2N = 448)."""
     os.environ['SSN_FORCE_SMEM_KERNEL'] = '1'
