@@ -7,9 +7,9 @@
 //     nothing but  wait panel -> FFMA2 contraction -> 32-lane reduce-scatter -> hand one dv per
 //     lane to their update warp through shared memory;
 //   * 8 UPDATE warps (warp u serves contraction warp u) own the float64 state (r, r_ref, v_ref in
-//     registers), evaluate f from the tables, apply the Euler step and the stopping tests and write
-//     the new panel block; after a named barrier of the update warps, warp p sends the CTA's slab
-//     (1296 bytes) to peer p with ONE cp.async.bulk;
+//     registers), evaluate f from the tables, apply the Euler step and the stopping tests, and
+//     publish the new r - r_ref (and the warp's flag word) to every CTA of the cluster with
+//     st.async remote stores that complete bytes on the destination's mbarrier;
 //   * the 8 stimuli of a panel run as TWO independent half-panel streams (stimuli 0..3 and 4..7;
 //     SSN_WS_INTERLEAVE=1: even / odd), each with its own double-buffered panel and mbarriers.
 //     While the update warps and the cluster exchange finish sweep k of one stream, the
@@ -61,21 +61,20 @@ namespace ssn {
 
 constexpr int WS_CW = 8;                                // contraction warps
 constexpr int WS_UW = 8;                                // update warps; warp u serves contraction warp u
-constexpr int WS_PAIRS = WS_UW / 2;                     // two update warps share a panel block
 constexpr int WS_THREADS = 32 * (WS_CW + WS_UW);
 constexpr int WS_TI = 7;                                // rows per contraction warp
 constexpr int WS_NP = WS_TI / 2;
-constexpr int WS_BLOCKS = MAX_CLUSTER * WS_PAIRS;       // panel blocks per buffer: (source CTA, warp pair)
-constexpr int WS_BLK_ROWS = 2 * WS_TI;                  // 14 float4 rows (four stimuli of the half) ...
-constexpr int WS_BLK_SLOTS = WS_BLK_ROWS + 8;           // ... + flag slot + padding: stride = rows (mod 8) keeps the
-                                                        // LDS.128 of 8 consecutive columns on 8 distinct bank groups
-constexpr int WS_BLK_BYTES = WS_BLK_SLOTS * 16;
-constexpr int WS_SLAB_BYTES = (WS_PAIRS - 1) * WS_BLK_BYTES + (WS_BLK_ROWS + 1) * 16;   // a CTA's blocks travel in one bulk copy
-constexpr int WS_ZERO_SLOT = WS_BLOCKS * WS_BLK_SLOTS;  // always-zero slot for the padded columns
-constexpr int WS_BUF_BYTES = (WS_ZERO_SLOT + 1) * 16;
-constexpr int WS_REG_C = SSN_WS_REG_C, WS_REG_U = SSN_WS_REG_U;            // 256 C + 128 U <= 384 * 168 (the CTA's allocation)
+// State panel of a stream (one buffer): per source CTA a slab of `slab_slots` 16-byte slots: the float4 (four
+// stimuli) of its WS_ROWS local rows, then the flag words of its update warps (two slots).
+// slab_slots = rows per CTA (mod 8) and >= WS_SLAB_USED keeps the LDS.128 of 8 consecutive columns on 8 distinct
+// 16-byte bank groups also where they straddle two CTAs.  The slot after the last slab is always zero.
+constexpr int WS_ROWS = WS_CW * WS_TI;                  // 56
+constexpr int WS_SLAB_USED = WS_ROWS + WS_UW / 4;       // rows + flag slots
+constexpr int WS_SLAB_MAX = WS_SLAB_USED + 7;
+constexpr int WS_BUF_BYTES = (MAX_CLUSTER * WS_SLAB_MAX + 1) * 16;
+__host__ __device__ constexpr int ws_slab_slots(int rpc) { return WS_SLAB_USED + (((rpc - WS_SLAB_USED) % 8) + 8) % 8; }
+constexpr int WS_REG_C = SSN_WS_REG_C, WS_REG_U = SSN_WS_REG_U;            // 256 C + 256 U <= 512 * 128 (the CTA's allocation)
 constexpr int WS_BAR_REFRESH = 1;                       // named barrier used by refresh events (all threads)
-constexpr int WS_BAR_UPDATE = 2;                        // named barrier of the update warps (publish)
 
 struct WsMisc {
     unsigned long long full[2][2];          // [half][buffer]: panel of the next sweep complete
@@ -107,7 +106,6 @@ __host__ __device__ inline WsSmem ws_smem_layout(int kpad, int n_sites, int tab_
 template <int R> __device__ __forceinline__ void reg_grow() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void reg_release() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void bar_sync_all(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WS_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_sync_update() { asm volatile("bar.sync %0, %1;" ::"n"(WS_BAR_UPDATE), "n"(32 * WS_UW) : "memory"); }
 
 template <int H> using HalfC = std::integral_constant<int, H>;
 // stimulus (0..7) handled by slot b (0..3) of stream h, and the stream's bit mask over the stimuli
@@ -115,18 +113,19 @@ __host__ __device__ constexpr int ws_stim(int h, int b) { return SSN_WS_INTERLEA
 __host__ __device__ constexpr unsigned ws_mask(int h) { return SSN_WS_INTERLEAVE ? (0x55u << h) : (0xfu << (4 * h)); }
 
 // OR of the flag words of all blocks of a panel buffer (absent blocks stay zero)
-__device__ __forceinline__ unsigned ws_flags(const unsigned char *buf_base, int lane) {
-    const uint2 f = *reinterpret_cast<const uint2 *>(buf_base + lane * WS_BLK_BYTES + WS_BLK_ROWS * 16);
+__device__ __forceinline__ unsigned ws_flags(const unsigned char *buf_base, int slab_slots, int lane) {
+    const uint2 f = *reinterpret_cast<const uint2 *>(buf_base + ((lane >> 2) * slab_slots + WS_ROWS) * 16 + (lane & 3) * 8);
     return __reduce_or_sync(0xffffffffu, f.x | f.y);
 }
 
 template <int NC>
 __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a) {
-    static_assert(WS_BLOCKS == 32, "one flag word per lane");
+    static_assert(MAX_CLUSTER * WS_UW == 64, "two flag words per lane");
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int csize = a.csize, dim = a.dim, kpad = a.kpad, rpc = a.rpc, N = a.n_sites;
+    const int slab_slots = ws_slab_slots(rpc);
     const WsSmem L = ws_smem_layout(kpad, N, rw_table_bytes(a.tab_nodes, a.tab2_nodes));
     float *xe = reinterpret_cast<float *>(smem + L.xe_off);
     double *tab = reinterpret_cast<double *>(smem + L.tab_off);
@@ -151,8 +150,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
     }
     if (tid == 0) {
         for (int h = 0; h < 2; ++h) {
-            mbar_init(smem_u32(&misc->full[h][0]), 2);             // the arming thread + the release-arrive of update warp 0
-            mbar_init(smem_u32(&misc->full[h][1]), 2);
+            mbar_init(smem_u32(&misc->full[h][0]), 1 + WS_UW);     // the arming thread + one release-arrive per update warp
+            mbar_init(smem_u32(&misc->full[h][1]), 1 + WS_UW);
             mbar_init(smem_u32(&misc->xfull[h]), 1);
             for (int w = 0; w < WS_CW; ++w) mbar_init(smem_u32(&misc->dvfull[h][w]), 1);
         }
@@ -165,7 +164,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
     cluster.sync();
 
     const volatile unsigned *pdelta = misc->pdelta;
-    const unsigned tx_bytes = (unsigned)((csize - 1) * WS_SLAB_BYTES);              // one slab from every peer
+    // bytes arriving from the peers per panel: 16 per row they own + their update warps' flag words
+    const unsigned tx_bytes = (unsigned)((dim - rows_here) * 16 + (csize - 1) * WS_UW * 4);
     const int n_chunks = (a.nb + TB - 1) / TB;
     auto full_bar = [&](int h, int b) { return smem_u32(&misc->full[h][b]); };
     auto panel = [&](int h, int b) { return smem + L.x_off + (h * 2 + b) * WS_BUF_BYTES; };
@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const int j = c * 32 + lane;
-            unsigned slot = WS_ZERO_SLOT;
+            unsigned slot = (unsigned)(MAX_CLUSTER * slab_slots);          // the zero slot
             if (j < dim) {
-                const int cta = j / rpc, lr = j - cta * rpc, u = lr / WS_BLK_ROWS, t = lr - u * WS_BLK_ROWS;
-                slot = (unsigned)((cta * WS_PAIRS + u) * WS_BLK_SLOTS + t);
+                const int cta = j / rpc, lr = j - cta * rpc;
+                slot = (unsigned)(cta * slab_slots + lr);
             }
             if (c & 1) colslot[c / 2] |= slot << 16; else colslot[c / 2] = slot;
         }
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                     unsigned char *xb = panel(h, buf);
                     // the flag word is loaded now and looked at after the contraction: finishing and refresh
                     // events are rare, so the contraction runs speculatively under the latency of the flag logic
-                    const uint2 fword2 = *reinterpret_cast<const uint2 *>(xb + lane * WS_BLK_BYTES + WS_BLK_ROWS * 16);
+                    const uint2 fword2 = *reinterpret_cast<const uint2 *>(xb + ((lane >> 2) * slab_slots + WS_ROWS) * 16 + (lane & 3) * 8);
                     const unsigned fword = fword2.x | fword2.y;
                     unsigned long long ap[WS_NP][4];
                     float as[4];
@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                                 if ((lane & 3) == b) exbuf[(h * WS_CW + cwarp) * 32 + lane] = mine;
                                 // r - r_ref is now zero for this stimulus on every row of every CTA
                                 float *col = reinterpret_cast<float *>(xb) + b;
-                                for (int q = ctid; q < WS_BLOCKS * WS_BLK_ROWS; q += 32 * WS_CW) {
-                                    const int blk = q / WS_BLK_ROWS, t = q - blk * WS_BLK_ROWS;
-                                    col[4 * (blk * WS_BLK_SLOTS + t)] = 0.f;
+                                for (int q = ctid; q < MAX_CLUSTER * WS_ROWS; q += 32 * WS_CW) {
+                                    const int cta = q / WS_ROWS, lr = q - cta * WS_ROWS;
+                                    col[4 * (cta * slab_slots + lr)] = 0.f;
                                 }
                             }
                             bar_sync_all(WS_BAR_REFRESH);
@@ -470,28 +470,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
         const int grow = row_base + lrow;
         const bool owner = my_t < WS_TI && lrow < rows_here;
         const double eps_own = grow < N ? a.eps_E : a.eps_I;
-        // panel block of the warp pair (u/2): rows of warp 2p in slots 0..6, of warp 2p+1 in slots 7..13, flag words in slot 14
-        const unsigned my_block = (unsigned)((rank * WS_PAIRS + (u >> 1)) * WS_BLK_BYTES);
-        const unsigned xoff = my_block + 16u * (unsigned)(WS_TI * (u & 1) + my_t) + 4u * (unsigned)my_b;
-        const unsigned foff = my_block + 16u * WS_BLK_ROWS + 4u * (unsigned)(u & 1);
-        const unsigned slab = (unsigned)(rank * WS_PAIRS * WS_BLK_BYTES);        // this CTA's blocks: one bulk copy per peer
+        const unsigned slab = (unsigned)(rank * slab_slots * 16);               // this CTA's slab in a panel buffer
+        const unsigned xoff = slab + 16u * (unsigned)lrow + 4u * (unsigned)my_b;
+        const unsigned foff = slab + 16u * WS_ROWS + 4u * (unsigned)u;
         unsigned ph = 0u, dvph = 0u;
 #if SSN_WS_PROFILE
         long long tc[6] = {0, 0, 0, 0, 0, 0};
 #endif
-        // after the warp's panel writes: fence for the async proxy, meet the other update warps, then warp p sends the
-        // CTA's slab to peer p and warp 0 releases the local contraction warps
-        auto publish = [&](int h, int nbuf) {
-            fence_proxy_async();
-            bar_sync_update();
-            if (lane == 0) {
-                if (u == 0) mbar_arrive_release(full_bar(h, nbuf));
-                if (u < csize - 1) {
-                    const int p = u + (u >= rank ? 1 : 0);                       // the csize-1 peers
-                    const unsigned src = x_local + (unsigned)((h * 2 + nbuf) * WS_BUF_BYTES) + slab;
-                    bulk_copy_to_peer(src + pdelta[p], src, WS_SLAB_BYTES, full_bar(h, nbuf) + pdelta[p]);
+        // Publish one value per lane (lanes 0..27: the new r - r_ref of their output; lane 28: the warp's flag word)
+        // to the same panel offset in every CTA of the cluster: a plain store at home, st.async (remote store that
+        // completes bytes on the destination's mbarrier) to the peers.  No proxy fence and no barrier among the
+        // update warps, unlike a cp.async.bulk of the slab (measured equal in throughput, ~500 cycles slower per
+        // exchange when a single stream is left).
+        const bool sender = owner || lane == 28;
+        const unsigned my_off = lane == 28 ? foff : xoff;
+        auto publish = [&](int h, int nbuf, unsigned bits) {
+            const unsigned off = (unsigned)((h * 2 + nbuf) * WS_BUF_BYTES) + my_off;
+            if (sender) {
+                *reinterpret_cast<unsigned *>(smem + L.x_off + off) = bits;
+#pragma unroll
+                for (int q = 0; q < MAX_CLUSTER - 1; ++q) {
+                    if (q < csize - 1) {
+                        const unsigned dlt = misc->pdelta[q + (q >= rank ? 1 : 0)];       // the csize-1 peers
+                        st_async_u32(x_local + off + dlt, bits, full_bar(h, nbuf) + dlt);
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_release(full_bar(h, nbuf));
         };
         for (;;) {
             cluster.sync();
@@ -530,10 +536,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                 for (int h = 0; h < 2; ++h) {
                     if (!((alive >> h) & 1u)) continue;
                     if (arming) mbar_arrive_expect_tx(full_bar(h, 0), tx_bytes);
-                    unsigned char *xb = panel(h, 0);
-                    if (owner) *reinterpret_cast<float *>(xb + xoff) = (float)sr[h];
-                    if (lane == 28) *reinterpret_cast<unsigned *>(xb + foff) = ws_mask(h) << 16;   // "big": no refresh yet
-                    publish(h, 0);
+                    publish(h, 0, lane == 28 ? ws_mask(h) << 16 : __float_as_uint((float)sr[h]));     // flags: "big", no refresh yet
                 }
 
                 auto ustep = [&](auto hc) {
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                     long long c1 = clock64(); tc[0] += c1 - c0;
 #endif
                     WS_TRACE(u == 0 && lane == 0, 3);
-                    const unsigned F = ws_flags(panel(h, buf), lane);
+                    const unsigned F = ws_flags(panel(h, buf), slab_slots, lane);
                     unsigned req, natural, conv_now, hard_now;
                     const bool go = advance(F, hm, it, done, force, req, natural, conv_now, hard_now);
                     if ((conv_now >> sid) & 1u) { my_status = 0; my_iters = it - 1; }
@@ -609,15 +612,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                     if (lv && r_cur >= a.r_hard) word |= 1u << (8 + st);
                     if (owner && ((lv && step >= tl) || !(tl > 0.0))) word |= 1u << (16 + st);   // exhausted ladder never asks
                     sr[h] = r_cur;
-                    unsigned char *xn_base = panel(h, nbuf);
-                    if (owner) *reinterpret_cast<float *>(xn_base + xoff) = (float)(r_cur - srref[h]);
+                    const float xn = (float)(r_cur - srref[h]);
 #if SSN_WS_PROFILE
                     long long c4 = clock64(); tc[3] += c4 - c3;
 #endif
                     WS_TRACE(u == 0 && lane == 0, 5);
                     word = __reduce_or_sync(0xffffffffu, word);
-                    if (lane == 28) *reinterpret_cast<unsigned *>(xn_base + foff) = word;
-                    publish(h, nbuf);
+                    publish(h, nbuf, lane == 28 ? word : __float_as_uint(xn));
 #if SSN_WS_PROFILE
                     tc[4] += clock64() - c4;
 #endif
