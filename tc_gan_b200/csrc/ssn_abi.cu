@@ -76,8 +76,24 @@ struct HostCtx {
         *out = slot[i];
         return 0;
     }
+    // pinned host staging (grown on demand): copies from it are truly asynchronous and do not serialise the
+    // calling threads inside the driver the way copies from pageable memory do
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+    int get_pinned(size_t bytes, void **out) {
+        if (pinned_cap < bytes) {
+            if (pinned) cudaFreeHost(pinned);
+            pinned = nullptr; pinned_cap = 0;
+            SSN_CUDA(cudaHostAlloc(&pinned, bytes, cudaHostAllocDefault));
+            pinned_cap = bytes;
+        }
+        *out = pinned;
+        return 0;
+    }
     void release() {
         for (void *p : slot) if (p) cudaFree(p);
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr; pinned_cap = 0;
         slot.clear(); cap.clear();
         if (stream) cudaStreamDestroy(stream);
         if (stream2) cudaStreamDestroy(stream2);
@@ -163,26 +179,33 @@ static int legacy_solve(int io_type, int N, double *W, double *ext, double k, do
     if (rc) return rc;
     const size_t dim = 2 * (size_t)N;
     cudaStream_t st = tl_ctx.stream;
-    GET(0, double, dim * dim, dW);
-    GET(1, double, dim, dE);
-    GET(2, double, dim, dR0);
+    GET(0, double, dim * dim + 2 * dim, dW);                 // W | ext | r0, uploaded with one copy
+    double *dE = dW + dim * dim, *dR0 = dE + dim;
     GET(3, double, dim, dR);
     GET(4, int, 2, dS);
-    SSN_CUDA(cudaMemcpyAsync(dW, W, dim * dim * sizeof(double), cudaMemcpyHostToDevice, st));
-    SSN_CUDA(cudaMemcpyAsync(dE, ext, dim * sizeof(double), cudaMemcpyHostToDevice, st));
-    SSN_CUDA(cudaMemcpyAsync(dR0, r0, dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    // stage through this thread's pinned buffer: [W | ext | r0 | result | status]
+    void *pin = nullptr;
+    if ((rc = tl_ctx.get_pinned((dim * dim + 3 * dim + 2) * sizeof(double), &pin))) return rc < 0 ? 1000 : rc;
+    double *hW = (double *)pin, *hE = hW + dim * dim, *hR0 = hE + dim, *hR = hR0 + dim;
+    int *hS = (int *)(hR + dim);
+    memcpy(hW, W, dim * dim * sizeof(double));
+    memcpy(hE, ext, dim * sizeof(double));
+    memcpy(hR0, r0, dim * sizeof(double));
+    SSN_CUDA(cudaMemcpyAsync(dW, hW, (dim * dim + 2 * dim) * sizeof(double), cudaMemcpyHostToDevice, st));
     ssn_solver sv = {};
     sv.io_type = io_type; sv.max_iter = max_iter; sv.k = k; sv.n = n;
     sv.tau_E = tau_E; sv.tau_I = tau_I; sv.dt = dt; sv.atol = atol;
     sv.rate_soft_bound = rate_soft_bound; sv.rate_hard_bound = rate_hard_bound;
-    rc = launch_fixed_point_f64(sv, 1, 1, N, dW, dE, 0, dR0, dR, dS, dS + 1, /*nonfinite_fixup=*/false, st);
+    int *counter = nullptr;
+    if ((rc = next_counter(&counter))) return rc < 0 ? 1000 : rc;
+    rc = launch_fixed_point_f64(sv, 1, 1, N, dW, dE, 0, dR0, dR, dS, dS + 1, /*nonfinite_fixup=*/false, counter, st);
     if (rc) return rc < 0 ? 1000 : rc;
-    int status[2] = {1, 0};
-    SSN_CUDA(cudaMemcpyAsync(r0, dR, dim * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SSN_CUDA(cudaMemcpyAsync(status, dS, sizeof(status), cudaMemcpyDeviceToHost, st));
+    SSN_CUDA(cudaMemcpyAsync(hR, dR, dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SSN_CUDA(cudaMemcpyAsync(hS, dS, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SSN_CUDA(cudaStreamSynchronize(st));
-    if (r1) memcpy(r1, r0, dim * sizeof(double));
-    return status[0];
+    memcpy(r0, hR, dim * sizeof(double));
+    if (r1) memcpy(r1, hR, dim * sizeof(double));
+    return hS[0];
 }
 
 }  // namespace ssn
@@ -266,7 +289,7 @@ int ssn_fixed_point_batch(const ssn_solver *solver, int nz, int nb, int n_sites,
         if ((rc = launch_convert_f32_to_f64(ext, dE, (size_t)(ext_per_network ? nz : 1) * nb * dim, st))) return rc;
         if (r_init && (rc = launch_convert_f32_to_f64(r_init, dR0, (size_t)nz * nb * dim, st))) return rc;
         if ((rc = launch_fixed_point_f64(*solver, nz, nb, n_sites, dW, dE, ext_per_network, r_init ? dR0 : nullptr,
-                                         dR, status, iters, true, st))) return rc;
+                                         dR, status, iters, true, counter, st))) return rc;
         if ((rc = launch_convert_f64_to_f32(dR, R, (size_t)nz * nb * dim, st))) return rc;
         // scratch is reused by the next call of this thread: make the stream order explicit
         return check_cuda(cudaStreamSynchronize(st), "precise device path");
@@ -351,8 +374,9 @@ int ssn_fixed_point_batch_f64(const ssn_solver *solver, int nz, int nb, int n_si
             SSN_CUDA(cudaMemcpyAsync(dR0, r_init + (size_t)z0 * nb * dim, nR * sizeof(double),
                                      cudaMemcpyHostToDevice, st));
         if (precise) {
+            if ((rc = next_counter(&counter))) return rc;
             rc = launch_fixed_point_f64(*solver, m, nb, n_sites, dW, dE, 0, r_init ? dR0 : nullptr, dR, dS,
-                                        dS + (size_t)slab * nb, true, st);
+                                        dS + (size_t)slab * nb, true, counter, st);
             if (rc) return rc;
         } else {
             float *fR0 = fR + (size_t)slab * nb * dim;

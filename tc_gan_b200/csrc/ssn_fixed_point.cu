@@ -509,8 +509,24 @@ int launch_fixed_point_f32(const ssn_solver &sv, int nz, int nb, int n_sites, in
 
 int launch_fixed_point_f64(const ssn_solver &sv, int nz, int nb, int n_sites, const double *W,
                            const double *ext, int ext_per_network, const double *r_init,
-                           double *R, int *status, int *iters, bool nonfinite_fixup, cudaStream_t stream) {
+                           double *R, int *status, int *iters, bool nonfinite_fixup, int *counter, cudaStream_t stream) {
     if (nz <= 0 || nb <= 0) return 0;
+    // W resident in cluster shared memory when it fits (SSN_F64=streamed forces the L2-streaming kernel)
+    const char *f64 = getenv("SSN_F64");
+    if (counter && !(f64 && !strcmp(f64, "streamed"))) {
+        const int rc = launch_fixed_point_f64_cluster(sv, nz, nb, n_sites, W, ext, ext_per_network, r_init, R, status,
+                                                      iters, counter, stream);
+        if (rc == 0) {
+            if (nonfinite_fixup) {
+                const int n_solves = nz * nb;
+                ssn_status_fixup_f64_kernel<<<(n_solves * 32 + 255) / 256, 256, 0, stream>>>(R, status, n_solves, 2 * n_sites);
+                SSN_CUDA(cudaGetLastError());
+                count_launch();
+            }
+            return 0;
+        }
+        if (rc != 1) return rc;
+    }
     Fp64Args a = {};
     a.nz = nz; a.nb = nb; a.n_sites = n_sites; a.dim = 2 * n_sites;
     a.W = W; a.ext = ext;

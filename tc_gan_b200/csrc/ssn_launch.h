@@ -9,7 +9,11 @@ int launch_fixed_point_f32(const ssn_solver &sv, int nz, int nb, int n_sites, in
                            float *R, int *status, int *iters, int *counter, cudaStream_t stream);
 int launch_fixed_point_f64(const ssn_solver &sv, int nz, int nb, int n_sites, const double *W,
                            const double *ext, int ext_per_network, const double *r_init,
-                           double *R, int *status, int *iters, bool nonfinite_fixup, cudaStream_t stream);
+                           double *R, int *status, int *iters, bool nonfinite_fixup, int *counter, cudaStream_t stream);
+// float64, W resident in the shared memory of a cluster; returns 1 when the shape does not fit
+int launch_fixed_point_f64_cluster(const ssn_solver &sv, int nz, int nb, int n_sites, const double *W,
+                                   const double *ext, int ext_per_network, const double *r_init,
+                                   double *R, int *status, int *iters, int *counter, cudaStream_t stream);
 int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters);
 // register-resident-W kernel; returns 1 when the shape is outside its range
 int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,

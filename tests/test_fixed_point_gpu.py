@@ -268,6 +268,54 @@ def test_lockstep_register_kernel(ssn, oracle):
         del os.environ['SSN_K1']
 
 
+def test_reference_abi_from_a_thread_pool(ssn, oracle):
+    """The reference drives solve_dynamics_*_euler from cpu_count() threads with the GIL released
+    (tc_gan/ssnode.py:455-460): concurrent calls must not disturb each other (per-thread stream, device and
+    pinned staging), and every result must equal the float64 oracle."""
+    from concurrent.futures import ThreadPoolExecutor
+    n_sites = 51
+    _, W, exts = seeded_problem(oracle, n_sites, 4, seed=31)
+    jobs = [(z, b) for z in range(len(W)) for b in range(len(exts))]
+    ref = {}
+    for z, b in jobs:
+        x, code, it = oracle.fixed_point(W[z], exts[b])
+        ref[(z, b)] = (x, code)
+
+    def solve(job):
+        z, b = job
+        return job, ssn.fixed_point(W[z], exts[b], k=0.01, n=2.2)
+
+    for rounds in range(2):
+        with ThreadPoolExecutor(8) as pool:
+            for job, sol in pool.map(solve, jobs):
+                x, code = ref[job]
+                assert sol.error == code
+                np.testing.assert_allclose(sol.x, x, rtol=0, atol=1e-10)
+
+
+def test_float64_streaming_fallback(ssn, oracle):
+    """The float64 kernel that streams W from L2 (used when the slice does not fit in cluster shared memory;
+    forced here with SSN_F64=streamed) gives the same results as the cluster-resident one."""
+    _, W, exts = seeded_problem(oracle, 33, 3, seed=32)
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+    os.environ['SSN_F64'] = 'streamed'
+    try:
+        Rp, errp, itsp = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, precise=True)
+    finally:
+        del os.environ['SSN_F64']
+    np.testing.assert_array_equal(errp, st_o)
+    np.testing.assert_array_equal(itsp, it_o)
+    np.testing.assert_allclose(Rp, Ro, rtol=0, atol=1e-10)
+    # a size whose double-precision slice exceeds shared memory with an 8-stimulus panel takes that path by itself
+    n_sites = 220
+    _, W, exts = seeded_problem(oracle, n_sites, 1, seed=33)
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+    Rp, errp, itsp = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, precise=True)
+    np.testing.assert_array_equal(errp, st_o)
+    np.testing.assert_array_equal(itsp, it_o)
+    np.testing.assert_allclose(Rp, Ro, rtol=0, atol=1e-10)
+
+
 def test_shared_memory_fallback_kernel(ssn, oracle):
     """The cluster/DSMEM kernel that keeps W in shared memory (used beyond 2N = 448)."""
     os.environ['SSN_FORCE_SMEM_KERNEL'] = '1'
