@@ -10,15 +10,16 @@
 //     registers), evaluate f from the tables, apply the Euler step and the stopping tests, and
 //     publish the new r - r_ref (and the warp's flag word) to every CTA of the cluster with
 //     st.async remote stores that complete bytes on the destination's mbarrier;
-//   * the 8 stimuli of a panel run as TWO independent half-panel streams (stimuli 0..3 and 4..7;
-//     SSN_WS_INTERLEAVE=1: even / odd), each with its own double-buffered panel and mbarriers.
-//     While the update warps and the cluster exchange finish sweep k of one stream, the
-//     contraction warps are already in sweep k of the other, so the float64 update, the publish
-//     and the DSMEM latency run under FMA work instead of after it.
+//   * the stimuli of a network run as TWO independent streams of half-panels (4 stimuli), each stream with
+//     its own double-buffered panel and mbarriers.  While the update warps and the cluster exchange finish
+//     sweep k of one stream, the contraction warps are already in sweep k of the other, so the float64
+//     update, the publish and the DSMEM latency run under FMA work instead of after it.  A stream whose
+//     half-panel has converged picks up the next half-panel of the network (nb > 8), so both streams stay
+//     busy until the network runs out of stimuli; only then does the last stream run alone.
 //
 // Register budget: the CTA starts with 128 registers per thread (512 threads); the update warp
 // groups release down to WS_REG_U and the contraction warp groups grow to WS_REG_C with
-// setmaxnreg (256 * 192 + 256 * 64 = the CTA's 65536), which is what lets a 98-register W tile
+// setmaxnreg (256 * 184 + 256 * 72 = the CTA's 65536), which is what lets a 98-register W tile
 // coexist with a second set of warps.  (This file must NOT be compiled with -rdc: ptxas ignores
 // setmaxnreg in relocatable device code.)
 //
@@ -46,12 +47,9 @@
 #ifndef SSN_WS_PF
 #define SSN_WS_PF 2          // panel columns loaded this many columns ahead of use
 #endif
-#ifndef SSN_WS_INTERLEAVE
-#define SSN_WS_INTERLEAVE 0  // stream h takes stimuli h, h+2, h+4, h+6 (0: stimuli 4h..4h+3)
-#endif
 #ifndef SSN_WS_REG_C
-#define SSN_WS_REG_C 192
-#define SSN_WS_REG_U 64
+#define SSN_WS_REG_C 184
+#define SSN_WS_REG_U 72
 #endif
 #ifndef SSN_WS_U_FIRST
 #define SSN_WS_U_FIRST 0     // 1: update warps take the lowest warp ids
@@ -108,9 +106,9 @@ template <int R> __device__ __forceinline__ void reg_release() { asm volatile("s
 __device__ __forceinline__ void bar_sync_all(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WS_THREADS) : "memory"); }
 
 template <int H> using HalfC = std::integral_constant<int, H>;
-// stimulus (0..7) handled by slot b (0..3) of stream h, and the stream's bit mask over the stimuli
-__host__ __device__ constexpr int ws_stim(int h, int b) { return SSN_WS_INTERLEAVE ? 2 * b + h : 4 * h + b; }
-__host__ __device__ constexpr unsigned ws_mask(int h) { return SSN_WS_INTERLEAVE ? (0x55u << h) : (0xfu << (4 * h)); }
+// bit (in the done / force masks and the flag fields) of slot b (0..3) of stream h, and the stream's bit mask
+__host__ __device__ constexpr int ws_stim(int h, int b) { return 4 * h + b; }
+__host__ __device__ constexpr unsigned ws_mask(int h) { return 0xfu << (4 * h); }
 
 // OR of the flag words of all blocks of a panel buffer (absent blocks stay zero)
 __device__ __forceinline__ unsigned ws_flags(const unsigned char *buf_base, int slab_slots, int lane) {
@@ -138,7 +136,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
     const int row_base = rank * rpc;
     const int rows_here = max(0, min(rpc, dim - row_base));
     const unsigned x_local = smem_u32(smem + L.x_off), xe_local = smem_u32(xe);
-    const int sid = lane & 7;                                       // stimulus whose status this lane tracks
+    const int sid = lane & 3;                                       // slot (of either stream) whose status this lane tracks
 
     // ---- one-time setup (all warps) ----
     if (tid < MAX_CLUSTER) misc->pdelta[tid] = map_to_rank(x_local, (unsigned)(tid < csize ? tid : 0)) - x_local;
@@ -166,13 +164,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
     const volatile unsigned *pdelta = misc->pdelta;
     // bytes arriving from the peers per panel: 16 per row they own + their update warps' flag words
     const unsigned tx_bytes = (unsigned)((dim - rows_here) * 16 + (csize - 1) * WS_UW * 4);
-    const int n_chunks = (a.nb + TB - 1) / TB;
+    const int n_hp = (a.nb + 3) / 4;                        // half-panels (4 stimuli) of a network: the units the streams pull
     auto full_bar = [&](int h, int b) { return smem_u32(&misc->full[h][b]); };
     auto panel = [&](int h, int b) { return smem + L.x_off + (h * 2 + b) * WS_BUF_BYTES; };
 
-    // Per-half sweep bookkeeping, computed identically by both roles from the cluster-uniform flag word F.
-    // Returns false when the half has finished.  `it` is this half's sweep counter.
-    //   done / force: 8-bit masks over the stimuli of the panel; hm selects the half's four bits.
+    // Per-stream sweep bookkeeping, computed identically by both roles from the cluster-uniform flag word F.
+    // Returns false when the stream's half-panel has finished.  `it` is the half-panel's sweep counter.
+    //   done / force: 8-bit masks, bits 4h..4h+3 = the four stimulus slots of stream h (hm selects them).
+    // Both roles walk the streams in the same order (0, 1, 0, 1, ... over the live ones), so every decision taken
+    // here -- including which half-panel a finished stream picks up next -- is the same in all warps of the cluster.
     auto advance = [&](unsigned F, unsigned hm, int it, unsigned &done, unsigned &force, unsigned &req,
                        unsigned &natural, unsigned &conv_now, unsigned &hard_now) -> bool {
         conv_now = 0u; hard_now = 0u;
@@ -187,6 +187,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
         req = natural | (force & ~done & hm);
         force &= ~req;
         return true;
+    };
+
+    // slots of a stream working on half-panel hp that hold no stimulus (bits 0..3)
+    auto empty_slots = [&](int hp) -> unsigned {
+        const int n = a.nb - 4 * hp;
+        return n >= 4 ? 0u : (n <= 0 ? 0xfu : (0xfu << n) & 0xfu);
     };
 
     constexpr bool U_FIRST = SSN_WS_U_FIRST != 0;
@@ -259,13 +265,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                 }
             }
 
-            for (int chunk = 0; chunk < n_chunks; ++chunk) {
-                const int nact = min(TB, a.nb - chunk * TB);
-                unsigned done = nact >= TB ? 0u : (0xffu << nact) & 0xffu;
+            {
+                // stream h starts on half-panel h; a stream that finishes picks up the next one of this network
+                int next_hp = min(2, n_hp);
+                unsigned done = empty_slots(0) | (empty_slots(1) << 4);
                 unsigned force = a.r_init ? (~done & 0xffu) : 0u;
-                unsigned alive = ((done & ws_mask(0)) != ws_mask(0) ? 1u : 0u) | ((done & ws_mask(1)) != ws_mask(1) ? 2u : 0u);
+                unsigned alive = n_hp > 1 ? 3u : 1u;
                 unsigned bufbits = 0u;
                 int it0 = 1, it1 = 1;
+                // the stream's half-panel is finished: take the next one (after a cluster barrier: nobody may publish
+                // the new panel while a slower CTA still looks at the flags of the old one) or retire the stream
+                auto c_finish = [&](int h) {
+                    if (next_hp < n_hp) {
+                        cluster.sync();
+                        const unsigned hm = ws_mask(h);
+                        done = (done & ~hm) | (empty_slots(next_hp) << (4 * h));
+                        force = (force & ~hm) | (a.r_init ? (~done & hm) : 0u);
+                        ++next_hp;
+                        (h ? it1 : it0) = 1;
+                        bufbits ^= 1u << h;                 // the new initial panel arrives in the other buffer
+                    } else {
+                        alive &= ~(1u << h);
+                    }
+                };
 
                 auto cstep = [&](auto hc) {
                     constexpr int h = decltype(hc)::value;
@@ -370,13 +392,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                     contract();
                     {
                         const unsigned F = __reduce_or_sync(0xffffffffu, fword);
-                        if (!advance(F, hm, it, done, force, req, natural, conv_now, hard_now)) { alive &= ~(1u << h); return; }
+                        if (!advance(F, hm, it, done, force, req, natural, conv_now, hard_now)) { c_finish(h); return; }
                     }
                     if (req) { refresh(req); contract(); }
 #else
                     {
                         const unsigned F = __reduce_or_sync(0xffffffffu, fword);
-                        if (!advance(F, hm, it, done, force, req, natural, conv_now, hard_now)) { alive &= ~(1u << h); return; }
+                        if (!advance(F, hm, it, done, force, req, natural, conv_now, hard_now)) { c_finish(h); return; }
                     }
                     if (req) refresh(req);
                     contract();
@@ -450,7 +472,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                     if (alive & 1u) cstep(HalfC<0>{});
                     if (alive & 2u) cstep(HalfC<1>{});
                 }
-                // nobody may publish the next panel while a slower CTA still reads this one
+                // nobody may publish the next network's panels while a slower CTA still reads these
                 cluster.sync();
             }
         }
@@ -505,39 +527,63 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
             if (net >= a.nz) break;
             const float *ext_net = a.ext + (size_t)net * a.ext_stride_z;
 
-            for (int chunk = 0; chunk < n_chunks; ++chunk) {
-                const int b0 = chunk * TB;
-                const int nact = min(TB, a.nb - b0);
-                unsigned done = nact >= TB ? 0u : (0xffu << nact) & 0xffu;
+            {
+                // stream h starts on half-panel h; a stream that finishes picks up the next one of this network
+                int next_hp = min(2, n_hp);
+                int hp0 = 0, hp1 = 1;                                        // half-panel of each stream
+                unsigned done = empty_slots(0) | (empty_slots(1) << 4);
                 unsigned force = a.r_init ? (~done & 0xffu) : 0u;
-                unsigned alive = ((done & ws_mask(0)) != ws_mask(0) ? 1u : 0u) | ((done & ws_mask(1)) != ws_mask(1) ? 2u : 0u);
+                unsigned alive = n_hp > 1 ? 3u : 1u;
                 unsigned bufbits = 0u;
                 int it0 = 1, it1 = 1;
-                int my_status = 1, my_iters = a.max_iter;                   // of stimulus `sid`
+                int my_status[2] = {1, 1}, my_iters[2] = {a.max_iter, a.max_iter};   // of slot lane & 3 of each stream
 
                 // float64 state of the (stream, output) values a lane owns
                 double sr[2], srref[2], svref[2];
                 float sext[2];
                 unsigned levels = 0u;                                        // ladder level, 4 bits per stream
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                // (re)start stream h on half-panel hp: load the stimulus and the initial state of the owned output,
+                // publish the initial panel r - r_ref (= r_init, refreshed at once, or 0) into buffer `buf`
+                auto start_stream = [&](int h, int hp, int buf) {
                     double r0 = 0.0;
                     float e = 0.f;
-                    const int st = ws_stim(h, my_b);
-                    if (owner && st < nact) {
-                        e = __ldg(ext_net + (size_t)(b0 + st) * dim + grow);
-                        if (a.r_init) r0 = (double)__ldg(a.r_init + ((size_t)net * a.nb + b0 + st) * dim + grow);
+                    const int sabs = 4 * hp + my_b;                          // stimulus of my slot
+                    if (owner && sabs < a.nb) {
+                        e = __ldg(ext_net + (size_t)sabs * dim + grow);
+                        if (a.r_init) r0 = (double)__ldg(a.r_init + ((size_t)net * a.nb + sabs) * dim + grow);
                     }
                     sr[h] = r0; srref[h] = 0.0; svref[h] = (double)e; sext[h] = e;
-                }
-
-                // ---- publish the initial panels: r - r_ref (= r_init, refreshed at once, or 0) ----
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (!((alive >> h) & 1u)) continue;
-                    if (arming) mbar_arrive_expect_tx(full_bar(h, 0), tx_bytes);
-                    publish(h, 0, lane == 28 ? ws_mask(h) << 16 : __float_as_uint((float)sr[h]));     // flags: "big", no refresh yet
-                }
+                    levels &= ~(0xfu << (4 * h));
+                    my_status[h] = 1; my_iters[h] = a.max_iter;
+                    if (arming) mbar_arrive_expect_tx(full_bar(h, buf), tx_bytes);
+                    publish(h, buf, lane == 28 ? ws_mask(h) << 16 : __float_as_uint((float)r0));     // flags: "big", no refresh yet
+                };
+                // the stream's half-panel is finished: write its results, then take the next half-panel (after a
+                // cluster barrier, see the contraction role) or retire the stream
+                auto u_finish = [&](int h) {
+                    const int hp = h ? hp1 : hp0;
+                    const int sabs = 4 * hp + my_b;
+                    if (owner && sabs < a.nb) a.R[((size_t)net * a.nb + sabs) * dim + grow] = (float)sr[h];
+                    if (rank == 0 && u == 0 && lane < 4 && 4 * hp + lane < a.nb) {       // lane == slot for lanes 0..3
+                        a.status[(size_t)net * a.nb + 4 * hp + lane] = my_status[h];
+                        if (a.iters) a.iters[(size_t)net * a.nb + 4 * hp + lane] = my_iters[h];
+                    }
+                    if (next_hp < n_hp) {
+                        cluster.sync();
+                        const unsigned hm = ws_mask(h);
+                        done = (done & ~hm) | (empty_slots(next_hp) << (4 * h));
+                        force = (force & ~hm) | (a.r_init ? (~done & hm) : 0u);
+                        (h ? hp1 : hp0) = next_hp;
+                        (h ? it1 : it0) = 1;
+                        bufbits ^= 1u << h;                 // the new initial panel goes to the other buffer
+                        start_stream(h, next_hp, (bufbits >> h) & 1u);
+                        ++next_hp;
+                    } else {
+                        alive &= ~(1u << h);
+                    }
+                };
+                start_stream(0, 0, 0);
+                if (n_hp > 1) start_stream(1, 1, 0);
 
                 auto ustep = [&](auto hc) {
                     constexpr int h = decltype(hc)::value;
@@ -556,9 +602,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                     const unsigned F = ws_flags(panel(h, buf), slab_slots, lane);
                     unsigned req, natural, conv_now, hard_now;
                     const bool go = advance(F, hm, it, done, force, req, natural, conv_now, hard_now);
-                    if ((conv_now >> sid) & 1u) { my_status = 0; my_iters = it - 1; }
-                    if ((hard_now >> sid) & 1u) { my_status = 2; my_iters = it - 1; }
-                    if (!go) { alive &= ~(1u << h); return; }
+                    if ((conv_now >> (4 * h + sid)) & 1u) { my_status[h] = 0; my_iters[h] = it - 1; }
+                    if ((hard_now >> (4 * h + sid)) & 1u) { my_status[h] = 2; my_iters[h] = it - 1; }
+                    if (!go) { u_finish(h); return; }
                     if (arming) mbar_arrive_expect_tx(full_bar(h, nbuf), tx_bytes);
 
                     const int st = ws_stim(h, my_b);
@@ -632,16 +678,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                     if (alive & 2u) ustep(HalfC<1>{});
                 }
 
-                // ---- results ----
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int st = ws_stim(h, my_b);
-                    if (owner && st < nact) a.R[((size_t)net * a.nb + b0 + st) * dim + grow] = (float)sr[h];
-                }
-                if (rank == 0 && u == 0 && lane < nact) {                  // lane == sid for lanes 0..7
-                    a.status[(size_t)net * a.nb + b0 + lane] = my_status;
-                    if (a.iters) a.iters[(size_t)net * a.nb + b0 + lane] = my_iters;
-                }
+                // nobody may publish the next network's panels while a slower CTA still reads these
                 cluster.sync();
             }
         }
