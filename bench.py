@@ -437,9 +437,9 @@ def main():
             'roofline': {'bound': 'fp32_ffma', 'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
                          'frac': achieved / peak.value if peak.value else None,
                          # DRAM bytes of the kernel from the committed ncu capture (profiles/r01_k1_ncu_summary.json:
-                         # 43.09 MB read + 7.36 MB written for 66 networks = 764 KB per network; z alone is 646 KB, the rest is the
+                         # k1_v4_ws_final: 43.14 MB read + 6.89 MB written for 66 networks = 758 KB per network; z alone is 646 KB, the rest is the
                          # write-back of the per-network prologue's register spills)
-                         'traffic': 764.4e3 * nz, 'traffic_unit': 'B per launch (ncu dram__bytes, scaled per network)',
+                         'traffic': 758.0e3 * nz, 'traffic_unit': 'B per launch (ncu dram__bytes, scaled per network)',
                          'peak_source': 'measured in this run (ssn_measure_fp32_peak); nominal 148 SM x 128 FMA x 2 x clock',
                          'hbm': {'achieved_gbs': algo_bytes / (kernel_ms * 1e-3) * 1e-9,
                                  'peak_gbs': peaks.get('hbm_gbs', 6650.0),
