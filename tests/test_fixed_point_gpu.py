@@ -316,6 +316,47 @@ def test_float64_streaming_fallback(ssn, oracle):
     np.testing.assert_allclose(Rp, Ro, rtol=0, atol=1e-10)
 
 
+@pytest.mark.parametrize('seed', [11, 12])
+def test_randomised_shapes_and_solver_settings(ssn, oracle, seed):
+    """Random sizes (every cluster width), stimulus counts (partial and refilled half-panels), transfer functions,
+    tolerances, iteration caps, initial states and weight scales against the float64 oracle: same codes, same
+    sweep counts (to the tolerance of check_sweeps), same rates."""
+    from tc_gan_b200.weight_gen import generate_weight
+    rs = np.random.RandomState(seed)
+    for case in range(20):
+        n_sites = int(rs.choice([1, 2, 5, 13, 28, 29, 40, 56, 57, 84, 101, 130, 168, 201, 224]))
+        nb = int(rs.choice([1, 2, 3, 4, 5, 7, 8, 9, 12, 13, 16, 17, 23]))
+        nz = int(rs.randint(1, 4))
+        io_type = str(rs.choice(['asym_tanh', 'asym_tanh', 'asym_linear', 'asym_power']))
+        atol = float(rs.choice([1e-5, 1e-5, 1e-7, 3e-4]))
+        max_iter = int(rs.choice([10000, 10000, 300, 57]))
+        jds = oracle.new_JDS()
+        J = jds['J'] * float(rs.choice([1.0, 1.0, 1.3, 0.7]))
+        zs = rs.rand(nz, 2 * n_sites, 2 * n_sites)
+        W = np.array([generate_weight(n_sites, J, jds['D'], jds['S'], z) for z in zs])
+        exts = oracle.stimulus_input(np.sort(rs.rand(nb)), n_sites, contrasts=(float(rs.choice([5., 20., 40.])),))
+        r0 = rs.rand(2 * n_sites) * 5 if rs.rand() < 0.3 else None
+        kw = dict(io_type=io_type, atol=atol, max_iter=max_iter)
+        if io_type != 'asym_tanh':
+            kw['rate_stop_at'] = 200.0
+        if r0 is None:
+            Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8, **kw)
+        else:
+            Ro = np.empty((nz, nb, 2 * n_sites)); st_o = np.empty((nz, nb), int); it_o = np.empty((nz, nb), int)
+            for z in range(nz):
+                for b in range(nb):
+                    Ro[z, b], st_o[z, b], it_o[z, b] = oracle.fixed_point(W[z], exts[b], r0=r0, **kw)
+        R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2, r0=r0, **kw)
+        label = (case, n_sites, nb, nz, io_type, atol, max_iter, r0 is not None)
+        np.testing.assert_array_equal(err, st_o, err_msg=str(label))
+        conv = st_o == 0
+        if conv.any():
+            d_it = np.abs(its - it_o)[conv]
+            assert (d_it <= 1 + it_o[conv] // 1000).all(), (label, int(d_it.max()))
+            tol = (ATOL * np.maximum(1, it_o[..., None] / 1000.0) + RTOL * np.abs(Ro)) * max(1.0, atol / 1e-5)
+            assert (np.abs(R - Ro)[conv] <= tol[conv]).all(), (label, float((np.abs(R - Ro) / tol)[conv].max()))
+
+
 def test_shared_memory_fallback_kernel(ssn, oracle):
     """The cluster/DSMEM kernel that keeps W in shared memory (used beyond 2N = 448)."""
     os.environ['SSN_FORCE_SMEM_KERNEL'] = '1'
