@@ -101,7 +101,30 @@ struct HostCtx {
     }
     ~HostCtx() { release(); }
 };
-static thread_local HostCtx tl_ctx;
+// Contexts outlive the threads that use them: the reference creates a new thread pool per find_fixed_points
+// call (tc_gan/ssnode.py:455-460), and a fresh stream + device scratch + pinned buffer per new thread would
+// cost more than the solves.  A thread borrows a context on first use and returns it when it exits.
+static std::mutex g_ctx_mutex;
+static std::vector<HostCtx *> g_ctx_free;
+struct HostCtxHandle {
+    HostCtx *p = nullptr;
+    HostCtx &get() {
+        if (!p) {
+            std::lock_guard<std::mutex> lock(g_ctx_mutex);
+            if (!g_ctx_free.empty()) { p = g_ctx_free.back(); g_ctx_free.pop_back(); }
+            else p = new HostCtx();
+        }
+        return *p;
+    }
+    ~HostCtxHandle() {
+        if (p) {
+            std::lock_guard<std::mutex> lock(g_ctx_mutex);
+            g_ctx_free.push_back(p);                 // never destroyed: no CUDA calls at thread or process exit
+        }
+    }
+};
+static thread_local HostCtxHandle tl_handle;
+#define tl_ctx (tl_handle.get())
 
 #define GET(i, T, n, var) T *var = nullptr; { void *_p; int _rc = tl_ctx.get(i, (size_t)(n) * sizeof(T), &_p); if (_rc) return _rc; var = (T *)_p; }
 
