@@ -243,4 +243,4 @@ def smoke(oracle):
     dJ, dD, dS, _ = oracle.ift_param_gradient(R.detach().double().cpu().numpy(), W, z, exts,
                                                jds['J'], jds['D'], jds['S'], gR)
     for got, want in ((J.grad, dJ), (D.grad, dD), (S.grad, dS)):
-        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-3, atol=1e-3 * np.abs(want).max())
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.abs(want).max())

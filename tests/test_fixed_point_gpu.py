@@ -189,6 +189,22 @@ def test_ragged_shapes(ssn, oracle, n_sites, nz, nb):
     np.testing.assert_allclose(Rp, Ro, rtol=0, atol=1e-10)
 
 
+def test_fifty_stimuli_sixteen_networks(ssn, oracle):
+    """BASELINE configs[4] shape per network (2N=402, 5 contrasts x 10 bandwidths = 50 stimuli): every network
+    runs 13 half-panels through the two streams, i.e. 11 refills of the half-panel queue per network; 16 networks
+    so that more clusters than one wave are busy and the queue is exercised with differing convergence orders."""
+    n_sites, nz = 201, 16
+    _, W, exts = seeded_problem(oracle, n_sites, nz, seed=50, bandwidths=np.linspace(0, 1, 10),
+                                contrasts=(5, 10, 20, 30, 40))
+    assert len(exts) == 50
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=16)
+    R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2)
+    np.testing.assert_array_equal(err, st_o)
+    tol = ATOL * np.maximum(1, it_o[..., None] / 1000.0) + RTOL * np.abs(Ro)
+    assert (np.abs(R - Ro) <= tol).all(), float((np.abs(R - Ro) / tol).max())
+    check_sweeps(its, it_o)
+
+
 def test_initial_state_and_max_iter(ssn, oracle):
     n_sites = 20
     _, W, exts = seeded_problem(oracle, n_sites, 2, seed=1)
