@@ -116,6 +116,25 @@ SSN_API int ssn_fixed_point_batch_f64(const ssn_solver *solver, int nz, int nb, 
                               double *R, int *status, int *iters, int precise);
 
 /*
+ * The same solve for a LIST of float64 host matrices, one pointer per network (the reference's callers hold
+ * one numpy array per network, ssnode.py:436-447; nothing is concatenated on the caller's side).
+ *   items    nz pointers to row-major [2N][2N] matrices, float64 (items_f32 = 0) or float32 (= 1): W
+ *            (w_kind = SSN_W_DENSE), or z with W built on chip from jds (SSN_W_FROM_Z: a caller that owns
+ *            J, D, S ships z and skips its own W construction)
+ *   ext      float64 [nb][2N];  r_init float64 [nz][nb][2N] or NULL;  R float64 [nz][nb][2N] out
+ * The matrices are rounded to float32 by `host_threads` host threads (<= 0: up to 16) into pinned staging,
+ * slab by slab, while the GPU solves the previous slab (three pinned slabs, two streams): the fast FP32 kernel
+ * with float64 state, i.e. ssn_fixed_point_batch_f64(precise = 0) without its host-side bottlenecks.
+ */
+SSN_API int ssn_fixed_point_batch_ptrs(const ssn_solver *solver, int nz, int nb, int n_sites, int w_kind,
+                               const void *const *items, int items_f32, const ssn_jds *jds,
+                               const double *ext, const double *r_init, double *R, int *status, int *iters,
+                               int host_threads);
+/* dst[i * bytes ...] = the `bytes` bytes at items[i] (i < n), copied by several host threads: stacks the kept
+ * per-network arrays into the Zs array find_fixed_points returns (ssnode.py:503). */
+SSN_API int ssn_host_gather(const void *const *items, int n, size_t bytes, void *dst, int host_threads);
+
+/*
  * Implicit-function-theorem generator gradient at the fixed points:
  *   (I - W^T Phi) mu = g,   dL/dW = (Phi mu) r^T,   dL/dtheta = <dL/dW, dW/dtheta>
  * with Phi = diag f'(W r + ext) (SS_grad.py:45-59) and g = dL/dr.  The adjoint
@@ -164,13 +183,27 @@ SSN_API int ssn_euler_forward(const ssn_solver *solver, int nz, int nb, int n_si
  * dL/dS in grad[12] (float64, device, zeroed here).  `traj` and `gain` are the
  * arrays the forward call stored; `adj` is scratch of the same size as traj.
  * grad_ext (float32 [nz][nb][2N], may be NULL) receives dL/d ext = sum_t gain[t] * lambda_{t+1}.
+ * w_dev (device float32 [2], may be NULL): when given, the kernel multiplies w_dyn and w_rate by w_dev[0] and
+ * w_dev[1] read on the device, so that upstream scalar gradients need no device-to-host copy.
  */
 SSN_API int ssn_euler_backward(const ssn_solver *solver, int nz, int nb, int n_sites,
                        const float *z, const ssn_jds *jds,
                        int seqlen, int skip_steps, double rate_penalty_threshold,
-                       const float *grad_time_avg, double w_dyn, double w_rate,
+                       const float *grad_time_avg, double w_dyn, double w_rate, const float *w_dev,
                        const float *traj, const float *gain, float *adj,
                        double *grad, float *grad_ext, void *stream);
+
+/*
+ * Probes: tuning_curve[i][b] = rates[model_ids[i]][b][probes[i]] for i < batch -- the gather of
+ * networks/cwgan.py:96-99 (ConditionalProber; FixedProber networks/ssn.py:838-851 is the special case
+ * model_ids = repeat(arange(nz)), probes = tile(fixed probes)) -- and its gradient, the scatter-add of
+ * grad_out [batch][nb] into grad_rates [nz][nb][2N] (zeroed here), which is the dL/dr array
+ * ssn_euler_backward / ssn_ift_gradient_batch consume.  Device pointers; model_ids and probes are int32.
+ */
+SSN_API int ssn_probe_gather(const float *rates, const int *model_ids, const int *probes,
+                     int batch, int nz, int nb, int n_sites, float *out, void *stream);
+SSN_API int ssn_probe_scatter(const float *grad_out, const int *model_ids, const int *probes,
+                      int batch, int nz, int nb, int n_sites, float *grad_rates, void *stream);
 
 /* Build W [nz][2N][2N] (float32) from z on the device (weight_gen.py:13-26). */
 SSN_API int ssn_generate_weight(int nz, int n_sites, const float *z, const ssn_jds *jds,
@@ -182,6 +215,16 @@ SSN_API const char *ssn_last_error(void);           /* thread-local text of the 
 SSN_API int ssn_kernel_launches(void);              /* kernels launched by this library so far (process-wide) */
 /* clusters the fixed-point kernel keeps resident for a given size, and its cluster width */
 SSN_API int ssn_fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters);
+
+/* shape tag of the kernel the FP32 path runs for this size, e.g. "ssn_fp_ws_kernel<NC=14,CW=8,UW=8,TI=7>x8"
+ * (kernel<template shape> x cluster width): keys the committed ncu figures in profiles/ */
+SSN_API int ssn_fixed_point_kernel_name(int n_sites, char *buf, int cap);
+
+/* Per-kernel device time: after ssn_profile_enable(1) every launch of this library is bracketed by CUDA
+ * events on its own stream; ssn_profile_read waits for them and writes "kernel_name total_ms launches" lines
+ * (one per kernel, since the previous read) into buf, returning the number of distinct kernels. */
+SSN_API int ssn_profile_enable(int on);
+SSN_API int ssn_profile_read(char *buf, int cap);
 
 /* measured FP32 FFMA throughput of the current device (dependent-chain probe kernel), TFLOP/s:
  * the roofline denominator of the fixed-point kernel */

@@ -103,6 +103,13 @@ libssnode.ssn_fixed_point_batch_f64.argtypes = [
     c_void_p, c_void_p, c_void_p, c_int]
 libssnode.ssn_fixed_point_batch_f64.restype = c_int
 
+libssnode.ssn_fixed_point_batch_ptrs.argtypes = [
+    POINTER(SolverStruct), c_int, c_int, c_int, c_int, c_void_p, c_int, POINTER(JDSStruct), c_void_p, c_void_p,
+    c_void_p, c_void_p, c_void_p, c_int]
+libssnode.ssn_fixed_point_batch_ptrs.restype = c_int
+libssnode.ssn_host_gather.argtypes = [c_void_p, c_int, ctypes.c_size_t, c_void_p, c_int]
+libssnode.ssn_host_gather.restype = c_int
+
 libssnode.ssn_ift_gradient_batch.argtypes = [
     POINTER(SolverStruct), c_int, c_int, c_int, c_void_p, POINTER(JDSStruct), c_void_p, c_int,
     c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
@@ -115,13 +122,18 @@ libssnode.ssn_euler_forward.restype = c_int
 
 libssnode.ssn_euler_backward.argtypes = [
     POINTER(SolverStruct), c_int, c_int, c_int, c_void_p, POINTER(JDSStruct),
-    c_int, c_int, c_double, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p,
+    c_int, c_int, c_double, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
     c_void_p, c_void_p, c_void_p]
 libssnode.ssn_euler_backward.restype = c_int
 
 libssnode.ssn_generate_weight.argtypes = [c_int, c_int, c_void_p, POINTER(JDSStruct), c_void_p,
                                           c_int, c_void_p]
 libssnode.ssn_generate_weight.restype = c_int
+
+libssnode.ssn_probe_gather.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+libssnode.ssn_probe_gather.restype = c_int
+libssnode.ssn_probe_scatter.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+libssnode.ssn_probe_scatter.restype = c_int
 
 libssnode.ssn_device_count.argtypes = []
 libssnode.ssn_device_count.restype = c_int
@@ -132,6 +144,13 @@ libssnode.ssn_kernel_launches.restype = c_int
 libssnode.ssn_fixed_point_occupancy.argtypes = [c_int, int_ptr, int_ptr]
 libssnode.ssn_fixed_point_occupancy.restype = c_int
 
+libssnode.ssn_fixed_point_kernel_name.argtypes = [c_int, ctypes.c_char_p, c_int]
+libssnode.ssn_fixed_point_kernel_name.restype = c_int
+libssnode.ssn_profile_enable.argtypes = [c_int]
+libssnode.ssn_profile_enable.restype = c_int
+libssnode.ssn_profile_read.argtypes = [ctypes.c_char_p, c_int]
+libssnode.ssn_profile_read.restype = c_int
+
 libssnode.ssn_measure_fp32_peak.argtypes = [double_ptr]
 libssnode.ssn_measure_fp32_peak.restype = c_int
 
@@ -141,7 +160,7 @@ EXPORTED_SYMBOLS = (
     'ssn_fixed_point_batch', 'ssn_fixed_point_batch_f64', 'ssn_ift_gradient_batch',
     'ssn_euler_forward', 'ssn_euler_backward', 'ssn_generate_weight', 'ssn_device_count',
     'ssn_last_error', 'ssn_kernel_launches', 'ssn_fixed_point_occupancy',
-    'ssn_measure_fp32_peak')
+    'ssn_measure_fp32_peak', 'ssn_profile_enable', 'ssn_profile_read', 'ssn_probe_gather', 'ssn_probe_scatter', 'ssn_fixed_point_batch_ptrs', 'ssn_host_gather', 'ssn_fixed_point_kernel_name')
 
 
 class SSNLibraryError(RuntimeError):
@@ -156,3 +175,25 @@ def check_call(code, what):
 
 def kernel_launches():
     return int(libssnode.ssn_kernel_launches())
+
+
+def fixed_point_kernel_tag(n_sites):
+    buf = ctypes.create_string_buffer(256)
+    check_call(libssnode.ssn_fixed_point_kernel_name(int(n_sites), buf, len(buf)), 'ssn_fixed_point_kernel_name')
+    return buf.value.decode()
+
+
+def profile_enable(on=True):
+    """Bracket every kernel launch of the library with CUDA events on its stream (include/ssnode.h)."""
+    return int(libssnode.ssn_profile_enable(int(bool(on))))
+
+
+def profile_read():
+    """{kernel name: (total ms, launches)} since the previous read; waits for those launches."""
+    buf = ctypes.create_string_buffer(8192)
+    libssnode.ssn_profile_read(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, n = line.rsplit(' ', 2)
+        out[name] = (float(ms), int(n))
+    return out

@@ -6,7 +6,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include "ssn_launch.h"
 
@@ -29,19 +31,70 @@ int check_cuda(cudaError_t e, const char *what) {
     return 1000 + (int)e;
 }
 
-// ---- work-counter ring for device-pointer calls (one int per launch) ------------
-static std::mutex g_counter_mutex;
-static int *g_counters[64] = {nullptr};
-static int g_counter_pos[64] = {0};
+// ---- work counters for the persistent kernels (one int per launch) ----------------
+// A launch leases a slot of a per-device ring.  Device-pointer entry points are asynchronous, so a slot may
+// still be in use by a kernel of another stream when the ring wraps: every slot carries an event recorded
+// after the launch that used it, and the next lessee's stream waits on that event before its memset.
 constexpr int COUNTER_RING = 256;
+struct CounterSlot { cudaEvent_t done = nullptr; bool used = false, leased = false; };
+struct CounterRing { int *base = nullptr; int pos = 0; CounterSlot slot[COUNTER_RING]; };
+static std::mutex g_counter_mutex;
+static CounterRing g_rings[64];
 
-static int next_counter(int **out) {
-    int dev = 0;
-    SSN_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_counter_mutex);
-    if (!g_counters[dev]) SSN_CUDA(cudaMalloc(&g_counters[dev], COUNTER_RING * sizeof(int)));
-    *out = g_counters[dev] + (g_counter_pos[dev]++ % COUNTER_RING);
-    return 0;
+struct CounterLease {
+    int *ptr = nullptr;
+    int dev = -1, idx = -1;
+    cudaStream_t stream = nullptr;
+    int acquire(cudaStream_t st) {
+        release();
+        SSN_CUDA(cudaGetDevice(&dev));
+        stream = st;
+        std::lock_guard<std::mutex> lock(g_counter_mutex);
+        CounterRing &ring = g_rings[dev & 63];
+        if (!ring.base) SSN_CUDA(cudaMalloc(&ring.base, COUNTER_RING * sizeof(int)));
+        for (int tries = 0; tries < COUNTER_RING; ++tries) {
+            const int i = ring.pos++ % COUNTER_RING;
+            CounterSlot &s = ring.slot[i];
+            if (s.leased) continue;                       // another thread is between acquire and launch
+            if (!s.done) SSN_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            if (s.used) SSN_CUDA(cudaStreamWaitEvent(st, s.done, 0));
+            s.leased = true;
+            idx = i;
+            ptr = ring.base + i;
+            return 0;
+        }
+        set_error("work-counter ring exhausted (%d launches being enqueued at once)", COUNTER_RING);
+        return -1;
+    }
+    void release() {
+        if (idx < 0) return;
+        std::lock_guard<std::mutex> lock(g_counter_mutex);
+        CounterSlot &s = g_rings[dev & 63].slot[idx];
+        s.used = cudaEventRecord(s.done, stream) == cudaSuccess;
+        s.leased = false;
+        idx = -1;
+    }
+    ~CounterLease() { release(); }
+};
+
+// ---- optional per-kernel timing (ssn_profile_enable) -------------------------------
+// CUDA events around each launch, on the stream the kernel is launched on; read back (and reset) with
+// ssn_profile_read.  Off by default: two event records per launch are not free.
+static std::atomic<int> g_profile{0};
+struct TimedLaunch { const char *name; cudaEvent_t e0, e1; };
+static std::mutex g_profile_mutex;
+static std::vector<TimedLaunch> g_timed;
+
+KernelTimer::KernelTimer(const char *name, cudaStream_t st) : name_(name), stream_(st) {
+    if (!g_profile.load(std::memory_order_relaxed)) return;
+    if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) { e0_ = e1_ = nullptr; return; }
+    cudaEventRecord(e0_, stream_);
+}
+KernelTimer::~KernelTimer() {
+    if (!e0_) return;
+    cudaEventRecord(e1_, stream_);
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    g_timed.push_back({name_, e0_, e1_});
 }
 
 // ---- per-thread host staging ------------------------------------------------------
@@ -219,9 +272,10 @@ static int legacy_solve(int io_type, int N, double *W, double *ext, double k, do
     sv.io_type = io_type; sv.max_iter = max_iter; sv.k = k; sv.n = n;
     sv.tau_E = tau_E; sv.tau_I = tau_I; sv.dt = dt; sv.atol = atol;
     sv.rate_soft_bound = rate_soft_bound; sv.rate_hard_bound = rate_hard_bound;
-    int *counter = nullptr;
-    if ((rc = next_counter(&counter))) return rc < 0 ? 1000 : rc;
-    rc = launch_fixed_point_f64(sv, 1, 1, N, dW, dE, 0, dR0, dR, dS, dS + 1, /*nonfinite_fixup=*/false, counter, st);
+    CounterLease lease;
+    if ((rc = lease.acquire(st))) return rc < 0 ? 1000 : rc;
+    rc = launch_fixed_point_f64(sv, 1, 1, N, dW, dE, 0, dR0, dR, dS, dS + 1, /*nonfinite_fixup=*/false, lease.ptr, st);
+    lease.release();
     if (rc) return rc < 0 ? 1000 : rc;
     SSN_CUDA(cudaMemcpyAsync(hR, dR, dim * sizeof(double), cudaMemcpyDeviceToHost, st));
     SSN_CUDA(cudaMemcpyAsync(hS, dS, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -290,8 +344,9 @@ int ssn_fixed_point_batch(const ssn_solver *solver, int nz, int nb, int n_sites,
     const size_t dim = 2 * (size_t)n_sites;
     if (mem == SSN_MEM_DEVICE) {
         cudaStream_t st = (cudaStream_t)stream;
-        int *counter = nullptr;
-        if ((rc = next_counter(&counter))) return rc;
+        CounterLease lease;
+        if ((rc = lease.acquire(st))) return rc;
+        int *counter = lease.ptr;
         if (!precise)
             return launch_fixed_point_f32(*solver, nz, nb, n_sites, w_kind, w, jds, ext, ext_per_network, r_init,
                                           R, status, iters, counter, st);
@@ -387,6 +442,7 @@ int ssn_fixed_point_batch_f64(const ssn_solver *solver, int nz, int nb, int n_si
     GET(7, float, (size_t)slab * nb * dim * 2, fR);
     SSN_CUDA(cudaMemcpyAsync(dE, ext, (size_t)nb * dim * sizeof(double), cudaMemcpyHostToDevice, st));
     if (!precise && (rc = launch_convert_f64_to_f32(dE, fE, (size_t)nb * dim, st))) return rc;
+    CounterLease lease;
     int *counter = nullptr;
     for (int z0 = 0; z0 < nz; z0 += slab) {
         const int m = std::min(slab, nz - z0);
@@ -397,7 +453,8 @@ int ssn_fixed_point_batch_f64(const ssn_solver *solver, int nz, int nb, int n_si
             SSN_CUDA(cudaMemcpyAsync(dR0, r_init + (size_t)z0 * nb * dim, nR * sizeof(double),
                                      cudaMemcpyHostToDevice, st));
         if (precise) {
-            if ((rc = next_counter(&counter))) return rc;
+            if ((rc = lease.acquire(st))) return rc;
+            counter = lease.ptr;
             rc = launch_fixed_point_f64(*solver, m, nb, n_sites, dW, dE, 0, r_init ? dR0 : nullptr, dR, dS,
                                         dS + (size_t)slab * nb, true, counter, st);
             if (rc) return rc;
@@ -405,7 +462,8 @@ int ssn_fixed_point_batch_f64(const ssn_solver *solver, int nz, int nb, int n_si
             float *fR0 = fR + (size_t)slab * nb * dim;
             if ((rc = launch_convert_f64_to_f32(dW, fW, (size_t)m * dim * dim, st))) return rc;
             if (r_init && (rc = launch_convert_f64_to_f32(dR0, fR0, nR, st))) return rc;
-            if ((rc = next_counter(&counter))) return rc;
+            if ((rc = lease.acquire(st))) return rc;
+            counter = lease.ptr;
             rc = launch_fixed_point_f32(*solver, m, nb, n_sites, SSN_W_DENSE, fW, nullptr, fE, 0,
                                         r_init ? fR0 : nullptr, fR, dS, dS + (size_t)slab * nb, counter, st);
             if (rc) return rc;
@@ -419,6 +477,196 @@ int ssn_fixed_point_batch_f64(const ssn_solver *solver, int nz, int nb, int n_si
                                      cudaMemcpyDeviceToHost, st));
         SSN_CUDA(cudaStreamSynchronize(st));
     }
+    return 0;
+}
+
+// ---- streamed host path: what ssnode.find_fixed_points calls ------------------------------------
+// The reference hands the solver one float64 W (1.29 MB at 2N = 402) per network, each its own numpy array
+// (tc_gan/ssnode.py:436-447).  Here the caller passes the list of pointers as is: no concatenation on the Python
+// side.  Host threads round slab k+1 to float32 straight into pinned staging while the GPU solves slab k; three
+// pinned slabs rotate over two streams, so H2D, solve and D2H of neighbouring slabs overlap.
+}  // extern "C"
+namespace {
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (cap >= bytes) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        SSN_CUDA(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+        cap = bytes;
+        return 0;
+    }
+};
+struct StreamCtx {
+    int device = -1;
+    static constexpr int NBUF = 3;
+    PinnedBuf win[NBUF], rout[NBUF];
+    void *dwin[NBUF] = {nullptr, nullptr, nullptr}, *drout[NBUF] = {nullptr, nullptr, nullptr};
+    size_t dwin_cap[NBUF] = {0, 0, 0}, drout_cap[NBUF] = {0, 0, 0};
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t h2d_done[NBUF] = {nullptr, nullptr, nullptr}, out_done[NBUF] = {nullptr, nullptr, nullptr};
+    float *dext = nullptr;
+    size_t dext_cap = 0;
+    int prepare() {
+        int dev = 0;
+        SSN_CUDA(cudaGetDevice(&dev));
+        if (dev == device) return 0;
+        device = dev;                                   // (buffers of a previous device are abandoned, not freed)
+        for (int q = 0; q < NBUF; ++q) { win[q] = PinnedBuf(); rout[q] = PinnedBuf(); dwin[q] = drout[q] = nullptr; dwin_cap[q] = drout_cap[q] = 0; }
+        dext = nullptr; dext_cap = 0;
+        for (int q = 0; q < 2; ++q) SSN_CUDA(cudaStreamCreateWithFlags(&stream[q], cudaStreamNonBlocking));
+        for (int q = 0; q < NBUF; ++q) {
+            SSN_CUDA(cudaEventCreateWithFlags(&h2d_done[q], cudaEventDisableTiming));
+            SSN_CUDA(cudaEventCreateWithFlags(&out_done[q], cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    static int grow(void **p, size_t *cap, size_t bytes) {
+        if (*cap >= bytes) return 0;
+        if (*p) cudaFree(*p);
+        *p = nullptr; *cap = 0;
+        SSN_CUDA(cudaMalloc(p, bytes));
+        *cap = bytes;
+        return 0;
+    }
+};
+static std::mutex g_stream_ctx_mutex;
+static std::vector<StreamCtx *> g_stream_ctx_free;
+struct StreamCtxLease {
+    StreamCtx *p = nullptr;
+    StreamCtxLease() {
+        std::lock_guard<std::mutex> lock(g_stream_ctx_mutex);
+        if (!g_stream_ctx_free.empty()) { p = g_stream_ctx_free.back(); g_stream_ctx_free.pop_back(); }
+        else p = new StreamCtx();
+    }
+    ~StreamCtxLease() {
+        std::lock_guard<std::mutex> lock(g_stream_ctx_mutex);
+        g_stream_ctx_free.push_back(p);
+    }
+};
+
+// run fn(i) for i in [0, n) on up to `threads` host threads (the calling thread included)
+template <class F>
+static void parallel_for(int n, int threads, F fn) {
+    threads = std::max(1, std::min(threads, n));
+    if (threads == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<int> next{0};
+    auto body = [&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); };
+    std::vector<std::thread> pool;
+    pool.reserve(threads - 1);
+    for (int t = 1; t < threads; ++t) pool.emplace_back(body);
+    body();
+    for (auto &th : pool) th.join();
+}
+
+}  // namespace
+extern "C" {
+
+// dst[i] = copy of the `bytes` bytes at items[i], i < n, with several host threads (np.array() of a list of
+// per-network arrays is a single-threaded 1.3 GB copy at the benchmark size)
+int ssn_host_gather(const void *const *items, int n, size_t bytes, void *dst, int host_threads) {
+    if (n < 0 || (n > 0 && (!items || !dst))) { set_error("ssn_host_gather: bad arguments"); return -1; }
+    if (host_threads <= 0) host_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    parallel_for(n, host_threads, [&](int i) { memcpy((char *)dst + (size_t)i * bytes, items[i], bytes); });
+    return 0;
+}
+
+int ssn_fixed_point_batch_ptrs(const ssn_solver *solver, int nz, int nb, int n_sites, int w_kind,
+                               const void *const *items, int items_f32, const ssn_jds *jds, const double *ext,
+                               const double *r_init, double *R, int *status, int *iters, int host_threads) {
+    int rc = validate(solver, nz, nb, n_sites);
+    if (rc) return rc;
+    if (nz == 0 || nb == 0) return 0;
+    if (!items || !ext || !R || !status) { set_error("ssn_fixed_point_batch_ptrs: NULL argument"); return -1; }
+    if (w_kind == SSN_W_FROM_Z && !jds) { set_error("SSN_W_FROM_Z needs jds"); return -1; }
+    StreamCtxLease lease;
+    StreamCtx &c = *lease.p;
+    if ((rc = c.prepare())) return rc;
+    const size_t dim = 2 * (size_t)n_sites, wsz = dim * dim, rsz = (size_t)nb * dim;
+    // slab: large enough that the persistent kernel's tail (one wave of its ~15-22 resident clusters) is a small
+    // part of a launch, small enough that the first conversion and the last solve, which nothing overlaps, stay short
+    const int slab = std::min(nz, std::max(32, std::min(256, (int)((192u << 20) / (wsz * sizeof(float))))));
+    if (host_threads <= 0) host_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    const size_t out_ints = 2 * (size_t)nb;                               // status + iters per network
+    const size_t rin = r_init ? rsz : 0;
+    for (int q = 0; q < StreamCtx::NBUF; ++q) {
+        if ((rc = c.win[q].ensure((size_t)slab * (wsz + rin) * sizeof(float)))) return rc;
+        if ((rc = c.rout[q].ensure((size_t)slab * (rsz * sizeof(float) + out_ints * sizeof(int))))) return rc;
+        if ((rc = StreamCtx::grow(&c.dwin[q], &c.dwin_cap[q], (size_t)slab * (wsz + rin) * sizeof(float)))) return rc;
+        if ((rc = StreamCtx::grow(&c.drout[q], &c.drout_cap[q], (size_t)slab * (rsz * sizeof(float) + out_ints * sizeof(int))))) return rc;
+    }
+    if ((rc = StreamCtx::grow((void **)&c.dext, &c.dext_cap, rsz * sizeof(float)))) return rc;
+    {
+        std::vector<float> e32(rsz);
+        for (size_t i = 0; i < rsz; ++i) e32[i] = (float)ext[i];
+        SSN_CUDA(cudaMemcpy(c.dext, e32.data(), rsz * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    auto drain = [&](int q, int z0, int m) {                             // results of the slab that used buffer q
+        if (cudaEventSynchronize(c.out_done[q]) != cudaSuccess) return check_cuda(cudaGetLastError(), "streamed results");
+        const float *hr = (const float *)c.rout[q].p;
+        const int *hs = (const int *)(hr + (size_t)slab * rsz);
+        parallel_for(m, host_threads, [&](int i) {
+            double *dst = R + (size_t)(z0 + i) * rsz;
+            const float *src = hr + (size_t)i * rsz;
+            for (size_t e = 0; e < rsz; ++e) dst[e] = (double)src[e];
+        });
+        memcpy(status + (size_t)z0 * nb, hs, (size_t)m * nb * sizeof(int));
+        if (iters) memcpy(iters + (size_t)z0 * nb, hs + (size_t)slab * nb, (size_t)m * nb * sizeof(int));
+        return 0;
+    };
+    struct Pending { int q, z0, m; };
+    std::vector<Pending> pending;
+    int k = 0;
+    for (int z0 = 0; z0 < nz; z0 += slab, ++k) {
+        const int m = std::min(slab, nz - z0), q = k % StreamCtx::NBUF;
+        cudaStream_t st = c.stream[k & 1];
+        if (k >= StreamCtx::NBUF) {                                       // buffer q is about to be reused
+            const Pending p = pending.front();
+            pending.erase(pending.begin());
+            if ((rc = drain(p.q, p.z0, p.m))) return rc;                  // (out_done[q] also implies h2d_done[q])
+        }
+        float *hw = (float *)c.win[q].p;
+        float *hr0 = hw + (size_t)slab * wsz;
+        parallel_for(m, host_threads, [&](int i) {
+            float *dst = hw + (size_t)i * wsz;
+            if (items_f32) {
+                memcpy(dst, items[z0 + i], wsz * sizeof(float));
+            } else {
+                const double *src = (const double *)items[z0 + i];
+                for (size_t e = 0; e < wsz; ++e) dst[e] = (float)src[e];
+            }
+            if (r_init) {
+                const double *r0 = r_init + (size_t)(z0 + i) * rsz;
+                for (size_t e = 0; e < rsz; ++e) hr0[(size_t)i * rsz + e] = (float)r0[e];
+            }
+        });
+        float *dw = (float *)c.dwin[q], *dr0 = dw + (size_t)slab * wsz;
+        float *dr = (float *)c.drout[q];
+        int *ds = (int *)(dr + (size_t)slab * rsz);
+        SSN_CUDA(cudaMemcpyAsync(dw, hw, (size_t)m * wsz * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (r_init) SSN_CUDA(cudaMemcpyAsync(dr0, hr0, (size_t)m * rsz * sizeof(float), cudaMemcpyHostToDevice, st));
+        SSN_CUDA(cudaEventRecord(c.h2d_done[q], st));
+        {
+            CounterLease cl;
+            if ((rc = cl.acquire(st))) return rc;
+            rc = launch_fixed_point_f32(*solver, m, nb, n_sites, w_kind, dw, jds, c.dext, 0, r_init ? dr0 : nullptr,
+                                        dr, ds, ds + (size_t)slab * nb, cl.ptr, st);
+            if (rc) return rc;
+        }
+        float *hr = (float *)c.rout[q].p;
+        int *hs = (int *)(hr + (size_t)slab * rsz);
+        SSN_CUDA(cudaMemcpyAsync(hr, dr, (size_t)m * rsz * sizeof(float), cudaMemcpyDeviceToHost, st));
+        SSN_CUDA(cudaMemcpyAsync(hs, ds, (size_t)m * nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+        SSN_CUDA(cudaMemcpyAsync(hs + (size_t)slab * nb, ds + (size_t)slab * nb, (size_t)m * nb * sizeof(int),
+                                 cudaMemcpyDeviceToHost, st));
+        SSN_CUDA(cudaEventRecord(c.out_done[q], st));
+        pending.push_back({q, z0, m});
+    }
+    for (const Pending &p : pending)
+        if ((rc = drain(p.q, p.z0, p.m))) return rc;
     return 0;
 }
 
@@ -446,13 +694,16 @@ int ssn_ift_gradient_batch(const ssn_solver *solver, int nz, int nb, int n_sites
     if (rc) return rc;
     if (!jds) { set_error("jds is NULL"); return -1; }
     const size_t dim = 2 * (size_t)n_sites;
-    int *counter = nullptr;
-    if ((rc = next_counter(&counter))) return rc;
-    if (mem == SSN_MEM_DEVICE)
+    CounterLease lease;
+    if (mem == SSN_MEM_DEVICE) {
+        if ((rc = lease.acquire((cudaStream_t)stream))) return rc;
         return launch_ift_gradient(*solver, nz, nb, n_sites, z, *jds, ext, ext_per_network, R, g, rtol, grad, mu,
-                                   status, iters, grad_ext, counter, (cudaStream_t)stream);
+                                   status, iters, grad_ext, lease.ptr, (cudaStream_t)stream);
+    }
     if ((rc = tl_ctx.ensure_device())) return rc;
     cudaStream_t st = tl_ctx.stream;
+    if ((rc = lease.acquire(st))) return rc;
+    int *counter = lease.ptr;
     const size_t nR = (size_t)nz * nb * dim, nE = (size_t)(ext_per_network ? nz : 1) * nb * dim;
     GET(8, float, (size_t)nz * dim * dim, dz);
     GET(9, float, nE, de);
@@ -488,25 +739,43 @@ int ssn_euler_forward(const ssn_solver *solver, int nz, int nb, int n_sites, con
         set_error("bad euler arguments (seqlen=%d skip_steps=%d)", seqlen, skip_steps);
         return -1;
     }
-    int *counter = nullptr;
-    if ((rc = next_counter(&counter))) return rc;
+    CounterLease lease;
+    if ((rc = lease.acquire((cudaStream_t)stream))) return rc;
     return launch_euler_forward(*solver, nz, nb, n_sites, z, *jds, ext, ext_per_network, seqlen, skip_steps,
-                                rate_penalty_threshold, time_avg, penalties, traj, gain, counter,
+                                rate_penalty_threshold, time_avg, penalties, traj, gain, lease.ptr,
                                 (cudaStream_t)stream);
 }
 
 int ssn_euler_backward(const ssn_solver *solver, int nz, int nb, int n_sites, const float *z, const ssn_jds *jds,
                        int seqlen, int skip_steps, double rate_penalty_threshold, const float *grad_time_avg,
-                       double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
-                       double *grad, float *grad_ext, void *stream) {
+                       double w_dyn, double w_rate, const float *w_dev, const float *traj, const float *gain,
+                       float *adj, double *grad, float *grad_ext, void *stream) {
     int rc = validate(solver, nz, nb, n_sites);
     if (rc) return rc;
     if (!jds || !traj || !gain || !adj) { set_error("euler backward needs jds, traj, gain, adj"); return -1; }
-    int *counter = nullptr;
-    if ((rc = next_counter(&counter))) return rc;
+    CounterLease lease;
+    if ((rc = lease.acquire((cudaStream_t)stream))) return rc;
     return launch_euler_backward(*solver, nz, nb, n_sites, z, *jds, seqlen, skip_steps, rate_penalty_threshold,
-                                 grad_time_avg, w_dyn, w_rate, traj, gain, adj, grad, grad_ext, counter,
+                                 grad_time_avg, w_dyn, w_rate, w_dev, traj, gain, adj, grad, grad_ext, lease.ptr,
                                  (cudaStream_t)stream);
+}
+
+// ---- probes (output-side boundary) ---------------------------------------------------------
+int ssn_probe_gather(const float *rates, const int *model_ids, const int *probes, int batch, int nz, int nb,
+                     int n_sites, float *out, void *stream) {
+    if (!rates || !model_ids || !probes || !out || batch < 0 || nz < 0 || nb < 0 || n_sites < 1) {
+        set_error("ssn_probe_gather: bad arguments");
+        return -1;
+    }
+    return launch_probe_gather(rates, model_ids, probes, batch, nz, nb, 2 * n_sites, out, (cudaStream_t)stream);
+}
+int ssn_probe_scatter(const float *grad_out, const int *model_ids, const int *probes, int batch, int nz, int nb,
+                      int n_sites, float *grad_rates, void *stream) {
+    if (!grad_out || !model_ids || !probes || !grad_rates || batch < 0 || nz < 0 || nb < 0 || n_sites < 1) {
+        set_error("ssn_probe_scatter: bad arguments");
+        return -1;
+    }
+    return launch_probe_scatter(grad_out, model_ids, probes, batch, nz, nb, 2 * n_sites, grad_rates, (cudaStream_t)stream);
 }
 
 // ---- introspection ----------------------------------------------------------------------
@@ -519,6 +788,48 @@ const char *ssn_last_error(void) { return tl_error; }
 int ssn_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 int ssn_fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters) {
     return fixed_point_occupancy(n_sites, cluster_size, resident_clusters);
+}
+int ssn_fixed_point_kernel_name(int n_sites, char *buf, int cap) {
+    return fixed_point_kernel_name(n_sites, buf, cap);
+}
+int ssn_profile_enable(int on) {
+    const int was = g_profile.exchange(on ? 1 : 0);
+    if (!on) {
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        for (auto &t : g_timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+        g_timed.clear();
+    }
+    return was;
+}
+// "name total_ms launches\n" per kernel since the last read; waits for the recorded launches to finish.
+int ssn_profile_read(char *buf, int cap) {
+    std::vector<TimedLaunch> taken;
+    {
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        taken.swap(g_timed);
+    }
+    struct Acc { const char *name; double ms; int n; };
+    std::vector<Acc> acc;
+    for (auto &t : taken) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+            size_t i = 0;
+            for (; i < acc.size(); ++i) if (!strcmp(acc[i].name, t.name)) break;
+            if (i == acc.size()) acc.push_back({t.name, 0.0, 0});
+            acc[i].ms += ms; acc[i].n += 1;
+        } else {
+            cudaGetLastError();
+        }
+        cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
+    }
+    int used = 0;
+    if (buf && cap > 0) buf[0] = 0;
+    for (auto &a : acc) {
+        const int w = snprintf(buf ? buf + used : nullptr, buf && cap > used ? cap - used : 0, "%s %.6f %d\n", a.name, a.ms, a.n);
+        if (w < 0 || used + w >= cap) break;
+        used += w;
+    }
+    return (int)acc.size();
 }
 int ssn_measure_fp32_peak(double *tflops) {
     int dev = 0, sms = 0;

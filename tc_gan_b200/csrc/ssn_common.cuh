@@ -118,6 +118,20 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int check_cuda(cudaError_t e, const char *what);       // 0 or 1000 + e (and records text)
 
+// Scope around one kernel launch: with ssn_profile_enable(1) it records CUDA events on the launching
+// stream before and after, for ssn_profile_read (per-kernel device time inside bench.py); otherwise a no-op.
+class KernelTimer {
+public:
+    KernelTimer(const char *name, cudaStream_t stream);
+    ~KernelTimer();
+    KernelTimer(const KernelTimer &) = delete;
+    KernelTimer &operator=(const KernelTimer &) = delete;
+private:
+    const char *name_;
+    cudaStream_t stream_;
+    cudaEvent_t e0_ = nullptr, e1_ = nullptr;
+};
+
 #define SSN_CUDA(call)                                        \
     do {                                                      \
         int _rc = ::ssn::check_cuda((call), #call);           \

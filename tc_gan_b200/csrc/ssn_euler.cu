@@ -39,6 +39,7 @@ struct EulerArgs {
     // backward
     const float *g_avg;
     double w_dyn, w_rate;
+    const float *w_dev;                // optional device multipliers of (w_dyn, w_rate)
     const float *traj_in, *gain_in;
     float *adj, *grad_ext;
 };
@@ -182,6 +183,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                     if (valid[u] && active) a.time_avg[(size_t)net * slice + goff[u]] = (float)(avg[u] / T);
             } else {
                 // ---- adjoint recursion, k = seqlen .. 1 (array index tp = k - 1) ----
+                const double w_dyn = a.w_dev ? a.w_dyn * (double)__ldg(a.w_dev) : a.w_dyn;
+                const double w_rate = a.w_dev ? a.w_rate * (double)__ldg(a.w_dev + 1) : a.w_rate;
                 float gavg[TO], r_cur[TO], r_next[TO], gext[TO];
 #pragma unroll
                 for (int u = 0; u < TO; ++u) {
@@ -214,9 +217,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                                 double d = 0.0;
                                 if (k >= skip + 1) {
                                     d = (double)gavg[u];
-                                    if (r_cur[u] > a.threshold) d += a.w_rate;
-                                    if (k >= skip + 2) d += 2.0 * a.w_dyn * ((double)r_cur[u] - (double)r_prev);
-                                    if (k <= seqlen - 1) d -= 2.0 * a.w_dyn * ((double)r_next[u] - (double)r_cur[u]);
+                                    if (r_cur[u] > a.threshold) d += w_rate;
+                                    if (k >= skip + 2) d += 2.0 * w_dyn * ((double)r_cur[u] - (double)r_prev);
+                                    if (k <= seqlen - 1) d -= 2.0 * w_dyn * ((double)r_next[u] - (double)r_cur[u]);
                                 }
                                 lam = d + (1.0 - eps_own[u]) * state[u] + (double)y[u];
                             }
@@ -418,7 +421,10 @@ static int launch_euler(bool backward, EulerArgs &a, int n_sites, int nz, int *c
     if (max_clusters < 1) { set_error("euler kernel: no resident cluster"); return -1; }
     cfg.gridDim = dim3(std::min(max_clusters, nz) * a.shape.csize, 1, 1);
     SSN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-    SSN_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    {
+        KernelTimer kt(backward ? "ssn_euler_cluster_kernel_bwd" : "ssn_euler_cluster_kernel_fwd", stream);
+        SSN_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    }
     count_launch();
     return 0;
 }
@@ -447,20 +453,23 @@ int launch_euler_forward(const ssn_solver &sv, int nz, int nb, int n_sites, cons
 
 int launch_euler_backward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                           int seqlen, int skip_steps, double threshold, const float *grad_time_avg,
-                          double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
+                          double w_dyn, double w_rate, const float *w_dev, const float *traj, const float *gain, float *adj,
                           double *grad, float *grad_ext, int *counter, cudaStream_t stream) {
     SSN_CUDA(cudaMemsetAsync(grad, 0, 12 * sizeof(double), stream));
     if (nz <= 0 || nb <= 0) return 0;
     EulerArgs a = {};
     fill_common(a, sv, nz, nb, n_sites, z, jds, seqlen, skip_steps, threshold);
-    a.g_avg = grad_time_avg; a.w_dyn = w_dyn; a.w_rate = w_rate;
+    a.g_avg = grad_time_avg; a.w_dyn = w_dyn; a.w_rate = w_rate; a.w_dev = w_dev;
     a.traj_in = traj; a.gain_in = gain; a.adj = adj; a.grad_ext = grad_ext;
     int rc = launch_euler(true, a, n_sites, nz, counter, stream);
     if (rc) return rc;
     const int dim = 2 * n_sites, tiles = (dim + GT - 1) / GT;
-    ssn_bptt_param_grad_kernel<<<nz * tiles * tiles, 256, 0, stream>>>(
-        n_sites, (long long)seqlen * nb, adj, traj, z, a.wc, grad);
-    SSN_CUDA(cudaGetLastError());
+    {
+        KernelTimer kt("ssn_bptt_param_grad_kernel", stream);
+        ssn_bptt_param_grad_kernel<<<nz * tiles * tiles, 256, 0, stream>>>(
+            n_sites, (long long)seqlen * nb, adj, traj, z, a.wc, grad);
+        SSN_CUDA(cudaGetLastError());
+    }
     count_launch();
     return 0;
 }

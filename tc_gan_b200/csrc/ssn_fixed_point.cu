@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <mutex>
 #include "ssn_cluster_core.cuh"
+#include <cstdio>
 #include <cstring>
 #include "ssn_launch.h"
 
@@ -349,14 +350,20 @@ __global__ void ssn_status_fixup_f64_kernel(const double *R, int *status, int n_
 // host side
 // ------------------------------------------------------------------------------------
 
+// opt-in shared memory per block of the CURRENT device (queried per call: cheap, and correct with several
+// devices and threads, unlike a cached static)
 static int max_optin_smem() {
-    static int v = -1;
-    if (v < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) v = 0;
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
     }
     return v;
+}
+static bool force_smem_kernel() {
+    const char *k1 = getenv("SSN_K1");
+    return getenv("SSN_FORCE_SMEM_KERNEL") || (k1 && !strcmp(k1, "smem"));
 }
 
 typedef void (*FpKernel)(const FpArgs);
@@ -425,13 +432,10 @@ static int plan_fixed_point(int n_sites, int nz, FpLaunchPlan *plan) {
 }
 
 int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters) {
-    const char *k1 = getenv("SSN_K1");
-    const int first = getenv("SSN_FORCE_SMEM_KERNEL") ? 2 : !k1 ? 0 : !strcmp(k1, "regw") ? 1 : !strcmp(k1, "smem") ? 2 : 0;
-    if (first <= 1) {
+    if (!force_smem_kernel()) {
         ssn_solver sv = {};
         sv.io_type = SSN_IO_TANH; sv.k = 0.01; sv.n = 2.2; sv.rate_soft_bound = 200; sv.rate_hard_bound = 1000;
-        if (first <= 0 && ws_occupancy(sv, n_sites, cluster_size, resident_clusters) == 0) return 0;
-        if (regw_occupancy(sv, n_sites, cluster_size, resident_clusters) == 0) return 0;
+        if (ws_occupancy(sv, n_sites, cluster_size, resident_clusters) == 0) return 0;
     }
     FpLaunchPlan plan;
     int rc = plan_fixed_point(n_sites, 0, &plan);
@@ -441,23 +445,32 @@ int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters
     return 0;
 }
 
+int fixed_point_kernel_name(int n_sites, char *buf, int cap) {
+    if (!buf || cap < 1) return -1;
+    if (!force_smem_kernel()) {
+        ssn_solver sv = {};
+        sv.io_type = SSN_IO_TANH; sv.k = 0.01; sv.n = 2.2; sv.rate_soft_bound = 200; sv.rate_hard_bound = 1000;
+        if (ws_kernel_name(sv, n_sites, buf, cap) == 0) return 0;
+    }
+    FpLaunchPlan plan;
+    int rc = plan_fixed_point(n_sites, 0, &plan);
+    if (rc) return rc;
+    snprintf(buf, cap, "ssn_fp_cluster_kernel<rows=%d,KL=%d>x%d", plan.var.rows, plan.var.kl, plan.shape.csize);
+    return 0;
+}
+
 // All pointers are device pointers; `counter` is one int of scratch.
 int launch_fixed_point_f32(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
                            const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
                            float *R, int *status, int *iters, int *counter, cudaStream_t stream) {
     if (nz <= 0 || nb <= 0) return 0;
     const int n_solves_all = nz * nb;
-    // Kernel choice: the warp-specialised register kernel, else the lockstep register kernel, else the
-    // shared-memory kernel (shapes out of range return 1).  SSN_K1 = ws | regw | smem forces a starting point.
-    const char *k1 = getenv("SSN_K1");
-    const int first = getenv("SSN_FORCE_SMEM_KERNEL") ? 2 : !k1 ? 0 : !strcmp(k1, "regw") ? 1 : !strcmp(k1, "smem") ? 2 : 0;
+    // Kernel choice: the warp-specialised register kernel, else (shapes out of its range return 1) the
+    // shared-memory kernel.  SSN_K1=smem (or SSN_FORCE_SMEM_KERNEL) forces the latter.
     int rc = 1;
-    if (first <= 0)
+    if (!force_smem_kernel())
         rc = launch_fixed_point_ws(sv, nz, nb, n_sites, w_kind, w, jds, ext, ext_per_network, r_init, R, status, iters,
                                    counter, stream);
-    if (rc == 1 && first <= 1)
-        rc = launch_fixed_point_regw(sv, nz, nb, n_sites, w_kind, w, jds, ext, ext_per_network, r_init, R, status,
-                                     iters, counter, stream);
     if (rc == 0) {
         ssn_status_fixup_kernel<<<(n_solves_all * 32 + 255) / 256, 256, 0, stream>>>(R, status, n_solves_all, 2 * n_sites);
         SSN_CUDA(cudaGetLastError());
@@ -498,7 +511,10 @@ int launch_fixed_point_f32(const ssn_solver &sv, int nz, int nb, int n_sites, in
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SSN_CUDA(cudaLaunchKernelEx(&cfg, plan.var.fn, a));
+    {
+        KernelTimer kt("ssn_fp_cluster_kernel", stream);
+        SSN_CUDA(cudaLaunchKernelEx(&cfg, plan.var.fn, a));
+    }
     count_launch();
     const int n_solves = nz * nb;
     ssn_status_fixup_kernel<<<(n_solves * 32 + 255) / 256, 256, 0, stream>>>(R, status, n_solves, 2 * n_sites);
@@ -543,14 +559,17 @@ int launch_fixed_point_f64(const ssn_solver &sv, int nz, int nb, int n_sites, co
         set_error("float64 kernel: 2N=%d needs %zu B of shared memory", a.dim, smem);
         return -1;
     }
-    if (tbd == 1) {
-        SSN_CUDA(cudaFuncSetAttribute(ssn_fp64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ssn_fp64_kernel<1><<<nz * n_chunks, 512, smem, stream>>>(a);
-    } else {
-        SSN_CUDA(cudaFuncSetAttribute(ssn_fp64_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ssn_fp64_kernel<8><<<nz * n_chunks, 512, smem, stream>>>(a);
+    {
+        KernelTimer kt("ssn_fp64_kernel", stream);
+        if (tbd == 1) {
+            SSN_CUDA(cudaFuncSetAttribute(ssn_fp64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ssn_fp64_kernel<1><<<nz * n_chunks, 512, smem, stream>>>(a);
+        } else {
+            SSN_CUDA(cudaFuncSetAttribute(ssn_fp64_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ssn_fp64_kernel<8><<<nz * n_chunks, 512, smem, stream>>>(a);
+        }
+        SSN_CUDA(cudaGetLastError());
     }
-    SSN_CUDA(cudaGetLastError());
     count_launch();
     const int n_solves = nz * nb;
     if (!nonfinite_fixup) return 0;

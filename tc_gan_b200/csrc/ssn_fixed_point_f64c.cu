@@ -338,7 +338,10 @@ int launch_fixed_point_f64_cluster(const ssn_solver &sv, int nz, int nb, int n_s
     a.atol = sv.atol; a.r_hard = sv.rate_hard_bound;
     a.max_iter = sv.max_iter; a.check_hard = sv.io_type != SSN_IO_TANH;
     SSN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-    SSN_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    {
+        KernelTimer kt("ssn_fp64_cluster_kernel", stream);
+        SSN_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+    }
     count_launch();
     return 0;
 }

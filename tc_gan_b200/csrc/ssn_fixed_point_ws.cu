@@ -28,7 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
-#include "ssn_regw_common.cuh"
+#include "ssn_ws_common.cuh"
 #include "ssn_launch.h"
 
 #ifndef SSN_WS_PROFILE
@@ -761,6 +761,14 @@ int ws_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *resi
     return 0;
 }
 
+int ws_kernel_name(const ssn_solver &sv, int n_sites, char *buf, int cap) {
+    WsPlan plan;
+    int rc = plan_ws(sv, n_sites, 0, &plan);
+    if (rc) return rc;
+    snprintf(buf, cap, "ssn_fp_ws_kernel<NC=%d,CW=%d,UW=%d,TI=%d>x%d", plan.nc, WS_CW, WS_UW, WS_TI, plan.csize);
+    return 0;
+}
+
 // Returns 1 when the shape is outside this kernel's range (the caller then uses the lockstep
 // register kernel), 0 on success, otherwise an error code.
 int launch_fixed_point_ws(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
@@ -789,7 +797,10 @@ int launch_fixed_point_ws(const ssn_solver &sv, int nz, int nb, int n_sites, int
     SSN_CUDA(cudaMalloc(&a.dbg_out, 1280 * sizeof(long long)));
     SSN_CUDA(cudaMemset(a.dbg_out, 0, 1280 * sizeof(long long)));
 #endif
-    SSN_CUDA(cudaLaunchKernelEx(&cfg, plan.fn, a));
+    {
+        KernelTimer kt("ssn_fp_ws_kernel", stream);
+        SSN_CUDA(cudaLaunchKernelEx(&cfg, plan.fn, a));
+    }
     count_launch();
 #if SSN_WS_PROFILE
     {

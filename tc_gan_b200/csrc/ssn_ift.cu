@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                         const int gr = row_base + own0 + u;
                         const float e = __ldg(ext_net + (size_t)(b0 + my_stim) * dim + gr);
                         phi[u] = io_gain<float>(a.io, v[u] + e);
+                        if (!isfinite(phi[u])) phi[u] = 0.f;          // non-finite state of a rejected solve
                         g_own[u] = __ldg(a.g + sol * dim + gr);
                         mu[u] = (double)g_own[u];
                         gm = fmaxf(gm, fabsf(g_own[u]));
@@ -166,8 +167,22 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
 
             unsigned done = nact >= TB ? 0u : (0xffu << nact) & 0xffu;
             int my_status = 1, my_iters = a.max_iter;
+            // A solve whose dL/dr vanishes (e.g. a rejected network masked out by the caller) has mu = 0: it is
+            // finished before the first sweep and contributes nothing, whatever (possibly non-finite) state R holds.
+            unsigned dead = 0u;
+            for (int b = 0; b < TB; ++b) {
+                float gs = 0.f;
+                for (int p = 0; p < csize; ++p) gs = fmaxf(gs, __uint_as_float(reinterpret_cast<const unsigned *>(&misc->scale[0][p][0])[b]));
+                if (!(gs > 0.f)) dead |= 1u << b;
+            }
+            done |= dead;
+            if ((dead >> my_stim) & 1u) {
+                my_status = 0; my_iters = 0;
+#pragma unroll
+                for (int u = 0; u < TO; ++u) { mu[u] = 0.0; phi[u] = 0.f; g_own[u] = 0.f; }
+            }
             int buf = 1;
-            for (int it = 1; it <= a.max_iter; ++it) {
+            for (int it = 1; it <= a.max_iter && done != 0xffu; ++it) {
                 float acc[TI][TB], y[TO];
                 contract_panel<TI, KL>(acc, Wsm, X4, P, kpad, buf, wrow, kl);
                 reduce_scatter<TI, KL>(acc, y, kl);
@@ -224,7 +239,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
             // This CTA owns rows of W^T, i.e. columns j of W.  Panel `buf` holds (Phi mu)_i for every i.
             for (int i = tid; i < rows_here * TB; i += nthreads) {
                 const int r = i / TB, b = i % TB;
-                rsm[i] = b < nact ? __ldg(a.R + ((size_t)net * a.nb + b0 + b) * dim + row_base + r) : 0.f;
+                rsm[i] = (b < nact && !((dead >> b) & 1u)) ? __ldg(a.R + ((size_t)net * a.nb + b0 + b) * dim + row_base + r) : 0.f;
             }
             __syncthreads();
             const float4 *A0 = X4 + (buf * 2 + 0) * P, *A1 = A0 + P;
@@ -333,7 +348,10 @@ int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const
     if (max_clusters < 1) { set_error("ift kernel: no resident cluster"); return -1; }
     cfg.gridDim = dim3(std::min(max_clusters, nz) * a.shape.csize, 1, 1);
     SSN_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-    SSN_CUDA(cudaLaunchKernelEx(&cfg, var.fn, a));
+    {
+        KernelTimer kt("ssn_ift_cluster_kernel", stream);
+        SSN_CUDA(cudaLaunchKernelEx(&cfg, var.fn, a));
+    }
     count_launch();
     return 0;
 }

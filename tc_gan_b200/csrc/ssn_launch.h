@@ -15,16 +15,14 @@ int launch_fixed_point_f64_cluster(const ssn_solver &sv, int nz, int nb, int n_s
                                    const double *ext, int ext_per_network, const double *r_init,
                                    double *R, int *status, int *iters, int *counter, cudaStream_t stream);
 int fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters);
-// register-resident-W kernel; returns 1 when the shape is outside its range
-int launch_fixed_point_regw(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
-                            const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
-                            float *R, int *status, int *iters, int *counter, cudaStream_t stream);
+// shape tag of the kernel the FP32 path runs for this size, e.g. "ssn_fp_ws_kernel<NC=14,CW=8,UW=8,TI=7>x8"
+int fixed_point_kernel_name(int n_sites, char *buf, int cap);
+int ws_kernel_name(const ssn_solver &sv, int n_sites, char *buf, int cap);
 // warp-specialised register-resident-W kernel (default); returns 1 when the shape is outside its range
 int launch_fixed_point_ws(const ssn_solver &sv, int nz, int nb, int n_sites, int w_kind, const float *w,
                           const ssn_jds *jds, const float *ext, int ext_per_network, const float *r_init,
                           float *R, int *status, int *iters, int *counter, cudaStream_t stream);
 int ws_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *resident_clusters);
-int regw_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *resident_clusters);
 
 int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                         const float *ext, int ext_per_network, const float *R, const float *g, double rtol,
@@ -37,8 +35,14 @@ int launch_euler_forward(const ssn_solver &sv, int nz, int nb, int n_sites, cons
                          cudaStream_t stream);
 int launch_euler_backward(const ssn_solver &sv, int nz, int nb, int n_sites, const float *z, const ssn_jds &jds,
                           int seqlen, int skip_steps, double threshold, const float *grad_time_avg,
-                          double w_dyn, double w_rate, const float *traj, const float *gain, float *adj,
+                          double w_dyn, double w_rate, const float *w_dev, const float *traj, const float *gain, float *adj,
                           double *grad, float *grad_ext, int *counter, cudaStream_t stream);
+
+// tuning_curve[i][b] = rates[model_ids[i]][b][probes[i]] and its scatter-add gradient (zeroes grad_rates first)
+int launch_probe_gather(const float *rates, const int *model_ids, const int *probes, int batch, int nz, int nb,
+                        int dim, float *out, cudaStream_t stream);
+int launch_probe_scatter(const float *grad_out, const int *model_ids, const int *probes, int batch, int nz, int nb,
+                         int dim, float *grad_rates, cudaStream_t stream);
 
 int launch_generate_weight(int nz, int n_sites, const float *z, const ssn_jds &jds, float *W, cudaStream_t stream);
 int launch_convert_f64_to_f32(const double *src, float *dst, size_t n, cudaStream_t stream);

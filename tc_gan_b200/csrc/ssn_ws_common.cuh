@@ -1,6 +1,5 @@
-// Pieces shared by the register-resident-W fixed-point kernels (ssn_fixed_point_regw.cu: all warps in
-// lockstep; ssn_fixed_point_ws.cu: warp-specialised): kernel arguments, mbarrier / st.async / bulk-copy
-// wrappers, packed-pair FMA, and the float64 table evaluation of the transfer function.
+// Pieces of the register-resident-W fixed-point kernel (ssn_fixed_point_ws.cu): kernel arguments, mbarrier /
+// st.async / bulk-copy wrappers, packed-pair FMA, and the float64 table evaluation of the transfer function.
 #pragma once
 #include <cmath>
 #include <cstdlib>
@@ -29,7 +28,7 @@ struct RwArgs {
     float tab_end;                                     // v at the end of the power-law table
     double tab2_end;                                   // v at the end of the tanh table
     int dbg;                                           // development switches (SSN_DBG), 0 in production
-    long long *dbg_out;                                // phase cycle counters when dbg & 4
+    long long *dbg_out;                                // phase cycle counters of the profile builds
 };
 
 // ---- mbarrier / st.async helpers ---------------------------------------------------------

@@ -14,7 +14,12 @@ What it mirrors in the reference (tc_gan/networks/wgan.py unless noted):
   * defaults (seqlen 1200, skip_steps 1000, dt 0.1, tau (10, 1), rate_cost 0.01,
     rate_penalty_threshold 200)                                       :39-63
   * the fixed-point ("legacy") GAN of tc_gan/run/gan.py:617-672, 830-941: generator = fixed
-    points of sampled networks, rejected networks re-drawn, implicit gradient.
+    points of sampled networks, implicit gradient; a network that does not converge for every
+    stimulus is rejected and a fresh one drawn until `num_models` have converged, exactly as
+    `find_fixed_points` does (tc_gan/ssnode.py:468-487).  `max_redraw_rounds` bounds the loop
+    (a generator whose draws keep diverging raises instead of spinning), the solver's `max_iter`
+    bounds every diverging draw, and `SSNRejectionLimiter` semantics (tc_gan/drivers.py:214-255)
+    are available through `rejection_rate()`.
 Tuning curves fed to the critic are rates probed at `sample_sites`
 (gradient_expressions/utils.py:74-149, track_offset_identity=True layout).
 
@@ -81,7 +86,9 @@ class SSNWassersteinGAN(object):
                  critic_iters_init=50, critic_iters=5, lipschitz_cost=10.0,
                  gen_learning_rate=0.001, disc_learning_rate=0.001,
                  param_min=1e-3, param_max=10.0, seed=0, device='cuda', solver_kwargs=None,
-                 ssn_type='default', V=0.5, dist_in='bernoulli', V_min=0.0, V_max=1.0):
+                 ssn_type='default', V=0.5, dist_in='bernoulli', V_min=0.0, V_max=1.0,
+                 max_redraw_rounds=20, disc_rate_penalty_bound=-1.0,
+                 gen_update='adam-wgan', disc_update='adam-wgan', gen_update_config=None, disc_update_config=None):
         if mode not in ('fixed_point', 'bptt'):
             raise ValueError('Unknown mode: {}'.format(mode))
         if ssn_type not in ('default', 'heteroin', 'deg-heteroin'):
@@ -111,8 +118,11 @@ class SSNWassersteinGAN(object):
             v0 = np.broadcast_to(np.asarray(V, dtype=float), (2,)).copy() if ssn_type == 'heteroin' else float(np.asarray(V))
             self.V = torch.tensor(v0, dtype=torch.float64, device=self.device, requires_grad=True)
         self.gen_params = [self.J, self.D, self.S] + ([self.V] if self.V is not None else [])
-        self.opt_gen = torch.optim.Adam(self.gen_params, lr=gen_learning_rate, betas=(0.5, 0.9))
-        self.opt_disc = torch.optim.Adam(self.critic.parameters(), lr=disc_learning_rate, betas=(0.5, 0.9))
+        from .networks.wgan import Updater          # update rules by the reference's names (adam-wgan, rmsprop, ...)
+        self.gen_updater = Updater(gen_learning_rate, gen_update, gen_update_config or {})
+        self.disc_updater = Updater(disc_learning_rate, disc_update, disc_update_config or {})
+        self.max_redraw_rounds, self.disc_rate_penalty_bound = int(max_redraw_rounds), disc_rate_penalty_bound
+        self.draws = self.unused = 0
         self.rng = torch.Generator(device=self.device)
         rank, world = sdist.world()
         self.rng.manual_seed(seed * 1000 + rank)
@@ -128,35 +138,86 @@ class SSNWassersteinGAN(object):
         self.rejections = 0
 
     # ---- generator --------------------------------------------------------------------
-    def sample_z(self):
+    def sample_z(self, n=None):
         dim = 2 * self.num_sites
-        return torch.rand((self.local_models, dim, dim), generator=self.rng, device=self.device)
+        n = self.local_models if n is None else n
+        return torch.rand((n, dim, dim), generator=self.rng, device=self.device)
+
+    def rejection_rate(self):
+        """#rejections / #draws so far (what tc_gan/drivers.py:232 thresholds at 0.6)."""
+        return self.rejections / max(self.draws, 1)
 
     def tuning_curves(self, rates):
         return subsample_neurons(rates, self.sample_sites, track_offset_identity=True)
 
-    def stimulus(self, nz):
+    def input_noise(self, nz):
+        """z_in [nz, 2N] of the heteroin types (+-1 bernoulli or uniform in [-1, 1]); None otherwise."""
+        if self.V is None:
+            return None
+        shape = (nz, 2 * self.num_sites)
+        if self.dist_in == 'bernoulli':
+            return torch.randint(0, 2, shape, generator=self.rng, device=self.device).float() * 2 - 1
+        return torch.rand(shape, generator=self.rng, device=self.device) * 2 - 1
+
+    def stimulus(self, nz, zs_in=None):
         """[nb, 2N], or [nz, nb, 2N] scaled per neuron by 1 + V z_in for the heteroin types."""
         if self.V is None:
             return self.exts
-        shape = (nz, 2 * self.num_sites)
-        if self.dist_in == 'bernoulli':
-            zs_in = torch.randint(0, 2, shape, generator=self.rng, device=self.device).float() * 2 - 1
-        else:
-            zs_in = torch.rand(shape, generator=self.rng, device=self.device) * 2 - 1
+        if zs_in is None:
+            zs_in = self.input_noise(nz)
         return torch_ops.hetero_input(self.exts, zs_in, self.V)
 
+    def converged_networks(self, z):
+        """
+        Rejection sampling as `find_fixed_points` (tc_gan/ssnode.py:468-487): solve the networks `z`; every one
+        that fails for some stimulus is replaced by a fresh draw until `len(z)` have converged.  Runs without
+        autograd; returns (z_kept, zs_in_kept or None, R_kept), in the order the networks were accepted.
+        """
+        want = z.shape[0]
+        zs, noises, Rs = [], [], []
+        missing, rounds = want, 0
+        while missing > 0:
+            rounds += 1
+            if rounds > self.max_redraw_rounds:
+                raise RuntimeError('fixed-point generator: %d of %d networks still unconverged after %d rounds of '
+                                   're-drawing (rejection rate %.2f)' % (missing, want, self.max_redraw_rounds,
+                                                                         self.rejection_rate()))
+            zs_in = self.input_noise(z.shape[0])
+            with torch.no_grad():
+                R, status, _ = torch_ops.fixed_points(z, self.J, self.D, self.S, self.stimulus(z.shape[0], zs_in),
+                                                      solver=self.solver)
+            ok = (status == 0).all(dim=1)
+            n_ok = int(ok.sum())                       # the control flow needs the count (as the reference's does)
+            self.draws += z.shape[0]
+            self.rejections += z.shape[0] - n_ok
+            if n_ok > missing:                         # an over-drawn round: keep the first `missing` successes
+                self.unused += n_ok - missing          # (FixedPointsInfo.unused of the reference's pool)
+                ok &= torch.cumsum(ok.to(torch.int32), 0) <= missing
+                n_ok = missing
+            zs.append(z[ok]); Rs.append(R[ok])
+            if zs_in is not None:
+                noises.append(zs_in[ok])
+            missing -= n_ok
+            if missing > 0:
+                # draw for the acceptance rate seen so far (the reference's pool over-submits likewise,
+                # ssnode.py:468-487 resubmit_threshold), at most 4x the batch per round
+                accept = max((self.draws - self.rejections) / max(self.draws, 1), 0.05)
+                z = self.sample_z(int(min(4 * want, max(missing, np.ceil(missing / accept)))))
+        return torch.cat(zs), (torch.cat(noises) if noises else None), torch.cat(Rs)
+
     def generate(self, z, differentiable):
-        """(tuning curves [kept, nb * n_sites], dynamics_penalty, rate_penalty)."""
+        """(tuning curves [num local models, nb * n_sites], dynamics_penalty, rate_penalty)."""
+        if self.mode == 'fixed_point':
+            z, zs_in, R = self.converged_networks(z)
+            if differentiable:
+                # the implicit gradient needs only the fixed points: attach them to the graph
+                R = torch_ops.attach_fixed_point(z, self.J, self.D, self.S, self.stimulus(z.shape[0], zs_in), R,
+                                                 solver=self.solver)
+            zero = R.new_zeros(())
+            return self.tuning_curves(R), zero, zero
         ctx = torch.enable_grad() if differentiable else torch.no_grad()
         with ctx:
             exts = self.stimulus(z.shape[0])
-            if self.mode == 'fixed_point':
-                R, status, _ = torch_ops.ssn_fixed_point(z, self.J, self.D, self.S, exts, solver=self.solver)
-                ok = (status == 0).all(dim=1)                      # rejection of non-convergent networks
-                self.rejections += int((~ok).sum())
-                zero = R.new_zeros(())
-                return self.tuning_curves(R[ok]), zero, zero
             avg, dyn, rate = torch_ops.euler_ssn(
                 z, self.J, self.D, self.S, exts, rate_penalty_threshold=self.costs['rate_penalty_threshold'],
                 **dict(self.euler, **self.io))
@@ -168,23 +229,31 @@ class SSNWassersteinGAN(object):
         return self.data[idx]
 
     def train_discriminator(self):
-        fake, _, _ = self.generate(self.sample_z(), differentiable=False)
-        real = self.next_minibatch(max(len(fake), 1))
-        self.opt_disc.zero_grad(set_to_none=True)
+        fake, dyn, rate = self.generate(self.sample_z(), differentiable=False)
+        bound = self.disc_rate_penalty_bound
+        if bound > 0 and float(rate) > bound:               # tc_gan/networks/wgan.py:395-400: skip the critic update
+            return dict(is_discriminator=True, disc_loss=float('nan'), accuracy=float('nan'),
+                        rate_penalty=float(rate), dynamics_penalty=float(dyn))
+        real = self.next_minibatch(len(fake))
+        params = list(self.critic.parameters())
+        for p in params:
+            p.grad = None
         loss, accuracy = critic_loss(self.critic, fake.float(), real, self.lipschitz_cost, self.rng)
-        loss.backward()
+        (loss + self.disc_updater.penalty(params)).backward()
         rank, world = sdist.world()
         if world > 1:
-            for p in self.critic.parameters():
+            for p in params:
                 torch.distributed.all_reduce(p.grad)
                 p.grad /= world
-        self.opt_disc.step()
-        return dict(is_discriminator=True, disc_loss=float(loss.detach()), accuracy=float(accuracy))
+        self.disc_updater.step(params)
+        return dict(is_discriminator=True, disc_loss=float(loss.detach()), accuracy=float(accuracy),
+                    rate_penalty=float(rate), dynamics_penalty=float(dyn))
 
     def train_generator(self):
         tc, dyn, rate = self.generate(self.sample_z(), differentiable=True)
         loss = -self.critic(tc.float()).mean() + self.costs['dynamics_cost'] * dyn + self.costs['rate_cost'] * rate
-        self.opt_gen.zero_grad(set_to_none=True)
+        for p in self.gen_params:
+            p.grad = None
         for p in self.critic.parameters():
             p.requires_grad_(False)
         loss.backward()
@@ -196,7 +265,7 @@ class SSNWassersteinGAN(object):
         if self.V is not None and world > 1:
             torch.distributed.all_reduce(self.V.grad)
             self.V.grad /= world
-        self.opt_gen.step()
+        self.gen_updater.step(self.gen_params)
         with torch.no_grad():
             for p in (self.J, self.D, self.S):
                 p.clamp_(self.param_min, self.param_max)

@@ -17,6 +17,7 @@ There is no CPU solver in this module.
 from __future__ import print_function, division
 
 import collections
+import ctypes
 import itertools
 
 import numpy as np
@@ -253,6 +254,83 @@ def fixed_points_batch(Ws, exts, k, n, r0=None, tau=DEFAULT_PARAMS['tau'],
     return Rs, errors, iters
 
 
+class _Solutions(object):
+    """`FixedPointsInfo.solutions` of the batched finder: behaves as the reference's tuple (one list of `nb`
+    converged `FixedPointResult` per kept network, ssnode.py:503-510) but builds the result objects on access --
+    8192 Python objects per 1024-network call would cost more than the solves."""
+
+    def __init__(self, xs, its):
+        self._xs, self._its = xs, its
+
+    def __len__(self):
+        return len(self._xs)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return tuple(self[i] for i in range(*k.indices(len(self))))
+        return [_set_message(FixedPointResult(x, 0, int(i))) for x, i in zip(self._xs[k], self._its[k])]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _solve_drawn(drawn, exts, jds, precise, host_threads, **kwargs):
+    """One batched GPU call for a list of drawn (Z, W): the streamed pointer-list entry point for the default
+    FP32-contraction kernel (no concatenation of the per-network arrays), `fixed_points_batch` for `precise`."""
+    if precise:
+        Ws = np.array([np.asarray(W, dtype='double') for _, W in drawn]) if jds is None else np.array(
+            [_generate_weight_from_z(Z, jds) for Z, _ in drawn])
+        return fixed_points_batch(Ws, exts, precise=True, **kwargs)
+    solver = kwargs.pop('solver', 'euler')
+    if solver != 'euler':
+        raise ValueError("Unknown solver: {}".format(solver))
+    r0 = kwargs.pop('r0', None)
+    sv = clib.make_solver(**kwargs)
+    items = [np.asarray(Z if jds is not None else W) for Z, W in drawn]
+    f32 = all(it.dtype == np.float32 for it in items)                 # float32 z / W is staged without conversion
+    items = [np.ascontiguousarray(it, dtype=np.float32 if f32 else np.float64) for it in items]
+    nz, dim, nb = len(items), items[0].shape[0], len(exts)
+    for it in items:
+        assert it.shape == (dim, dim), 'every network must be (2N, 2N)'
+    assert exts.shape == (nb, dim) and dim % 2 == 0
+    ptrs = (ctypes.c_void_p * nz)(*[it.ctypes.data for it in items])
+    r_init = None
+    if r0 is not None:
+        r0 = np.asarray(r0, dtype='double')
+        if r0.any():
+            r_init = np.ascontiguousarray(np.broadcast_to(r0, (nz, nb, dim)))
+    Rs = np.empty((nz, nb, dim))
+    errors = np.empty((nz, nb), dtype=np.int32)
+    iters = np.empty((nz, nb), dtype=np.int32)
+    clib.check_call(libssnode.ssn_fixed_point_batch_ptrs(
+        sv, nz, nb, dim // 2, clib.W_FROM_Z if jds is not None else clib.W_DENSE, ptrs, int(f32),
+        None if jds is None else clib.make_jds(jds['J'], jds['D'], jds['S']), exts.ctypes.data,
+        None if r_init is None else r_init.ctypes.data, Rs.ctypes.data, errors.ctypes.data, iters.ctypes.data,
+        int(host_threads)), 'ssn_fixed_point_batch_ptrs')
+    return Rs, errors, iters
+
+
+def _stack(arrays, host_threads=0):
+    """np.array(arrays) -- with the copy spread over host threads when the elements are equal-shaped contiguous
+    ndarrays (the kept Z of a 1024-network call are 1.3 GB)."""
+    first = arrays[0]
+    if not (isinstance(first, np.ndarray) and first.nbytes >= 1 << 16 and len(arrays) > 1 and all(
+            isinstance(a, np.ndarray) and a.shape == first.shape and a.dtype == first.dtype and
+            a.flags['C_CONTIGUOUS'] for a in arrays)):
+        return np.array(arrays)
+    out = np.empty((len(arrays),) + first.shape, dtype=first.dtype)
+    ptrs = (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+    clib.check_call(libssnode.ssn_host_gather(ptrs, len(arrays), first.nbytes, out.ctypes.data, int(host_threads)),
+                    'ssn_host_gather')
+    return out
+
+
+def _generate_weight_from_z(Z, jds):
+    from .weight_gen import generate_weight
+    Z = np.asarray(Z, dtype='double')
+    return generate_weight(Z.shape[0] // 2, jds['J'], jds['D'], jds['S'], Z)
+
+
 def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
     """
     Find `num` sets of fixed points using weight matrices from `Z_W_gen`.
@@ -268,10 +346,16 @@ def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
     it, the kept networks are the first `num` successes in generator order
     (ssnode.py:489-495) and ``info.unused`` is 0.
 
-    Extra keyword arguments understood here (and ignored by nothing): those of
-    `fixed_point`, plus ``precise`` (float64 kernel), and the thread-pool knobs
-    ``no_pool``, ``resubmit_threshold``, ``deterministic`` which are accepted
-    and have no effect.
+    Extra keyword arguments understood here: those of `fixed_point`, plus
+
+    * ``precise`` -- float64 kernel instead of the FP32-contraction / float64-state one;
+    * ``jds=dict(J=, D=, S=)`` -- the generator's ``Z`` is the uniform noise z itself and W is built on
+      the GPU from (J, D, S): the ``W`` element of each pair is ignored (may be ``None``), so a caller
+      that owns the generator parameters skips its own weight construction and the float64 W never
+      crosses the bus;
+    * ``host_threads`` -- threads staging the matrices into pinned memory (default: up to 16);
+    * the thread-pool knobs ``no_pool``, ``resubmit_threshold``, ``deterministic``, which are accepted and
+      have no effect (there is no pool: results are always deterministic, nothing is over-submitted).
     """
     if method not in ('parallel', 'serial'):
         raise ValueError('Unknown method: {}'.format(method))
@@ -279,37 +363,39 @@ def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
     for ignored in ('no_pool', 'resubmit_threshold', 'deterministic'):
         kwargs.pop(ignored, None)
     check = kwargs.pop('check', False)
-    exts = np.asarray(exts, dtype='double')
-    nb = len(exts)
+    jds = kwargs.pop('jds', None)
+    precise = kwargs.pop('precise', False)
+    host_threads = kwargs.pop('host_threads', 0)
+    if 'io_type' in kwargs and kwargs['io_type'] not in _IO_TYPES:
+        raise ValueError("Unknown I/O type: {}".format(kwargs['io_type']))
+    exts = np.ascontiguousarray(exts, dtype='double')
     Z_W_gen = iter(Z_W_gen)
 
-    kept = []                       # (Z, Rs[nb, 2N], iters[nb])
+    kept_z, kept_R, kept_it = [], [], []
     counter = collections.Counter()
-    while len(kept) < num:
-        drawn = take(num - len(kept), Z_W_gen)
+    while len(kept_z) < num:
+        drawn = take(num - len(kept_z), Z_W_gen)
         if not drawn:
             break
-        Ws = np.array([np.asarray(W, dtype='double') for _, W in drawn])
-        Rs, errors, iters = fixed_points_batch(Ws, exts, **kwargs)
-        for (Z, _), R, err, its in zip(drawn, Rs, errors, iters):
-            if (err == 0).all():
-                kept.append((Z, R, its))
-                continue
+        Rs, errors, iters = _solve_drawn(drawn, exts, jds, precise, host_threads, **kwargs)
+        ok = (errors == 0).all(axis=1) & np.isfinite(Rs).all(axis=(1, 2))
+        for i in np.flatnonzero(~ok):
+            err = errors[i].copy()
+            err[(err == 0) & ~np.isfinite(Rs[i]).all(axis=1)] = 1          # ssnode.py:257-262
             # the reference visits stimuli last to first and records the first failure
             b = max(np.flatnonzero(err != 0))
-            sol = _set_message(FixedPointResult(R[b], int(err[b]), int(its[b])))
+            sol = _set_message(FixedPointResult(Rs[i, b], int(errors[i, b]), int(iters[i, b])))
             counter[sol.error] += 1
             if check:
                 raise sol.to_exception()
+        kept_z.extend(drawn[i][0] for i in np.flatnonzero(ok))
+        kept_R.append(Rs[ok])
+        kept_it.append(iters[ok])
 
-    if not kept:
+    if not kept_z:
         raise ValueError('find_fixed_points: Z_W_gen was exhausted before any network converged')
-    zs, xs, its = zip(*kept)
-    solutions = tuple(
-        [_set_message(FixedPointResult(x, 0, int(i))) for x, i in zip(R, it)]
-        for R, it in zip(xs, its))
-    return np.array(zs), np.array(xs), FixedPointsInfo(
-        solutions, counter, sum(counter.values()), 0)
+    xs, its = np.concatenate(kept_R), np.concatenate(kept_it)
+    return _stack(kept_z, host_threads), xs, FixedPointsInfo(_Solutions(xs, its), counter, sum(counter.values()), 0)
 
 
 def find_fixed_points_serial(num, Z_W_gen, exts, **common_kwargs):

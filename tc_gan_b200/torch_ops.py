@@ -14,15 +14,31 @@ These replace the Theano ops of the reference on the SSN path:
 torch is used for device memory, streams and autograd bookkeeping only; all
 arithmetic on the path is in the CUDA library.  CPU tensors are rejected.
 """
+import weakref
+
 import torch
 
 from . import clib
 from .clib import libssnode
 
 
+_jds_cache = {'refs': None, 'versions': None, 'struct': None}
+
+
 def _jds_struct(J, D, S):
-    return clib.make_jds(J.detach().double().cpu().numpy(), D.detach().double().cpu().numpy(),
-                         S.detach().double().cpu().numpy())
+    """Host copy of (J, D, S) for the kernels' by-value constants.  The device->host read drains the stream, so
+    it is done once per parameter VERSION: the cache is keyed on the identity of the three tensor objects (weak
+    references, so a recycled address can never alias) and their in-place version counters -- one read after
+    each optimizer step, none for repeated calls with unchanged parameters -- and uses a single copy.
+    (Writing through ``.data`` does not bump the version counter; use in-place ops under ``no_grad``.)"""
+    params = (J, D, S)
+    refs, versions = _jds_cache['refs'], tuple(t._version for t in params)
+    if refs is None or versions != _jds_cache['versions'] or any(r() is not t for r, t in zip(refs, params)):
+        flat = torch.cat([t.detach().reshape(-1).double() for t in params]).cpu().numpy()
+        _jds_cache['struct'] = clib.make_jds(flat[0:4], flat[4:8], flat[8:12])
+        _jds_cache['refs'] = tuple(weakref.ref(t) for t in params)
+        _jds_cache['versions'] = versions
+    return _jds_cache['struct']
 
 
 def _check_cuda(*tensors):
@@ -97,6 +113,29 @@ def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-6, return_mu=F
     return out
 
 
+# (status, iters) of the adjoint solves of the most recent implicit-gradient backward, device tensors
+# [nz, nb]: status 1 = the damped adjoint iteration hit max_iter (marginally stable fixed point).  Reading
+# them synchronises; `adjoint_failures()` does so on demand.
+last_adjoint = {'status': None, 'iters': None}
+
+
+def adjoint_failures():
+    st = last_adjoint['status']
+    return 0 if st is None else int((st != 0).sum())
+
+
+def _ift_backward(ctx, z, J, D, S, ext, R, grad_R):
+    need_ext = ctx.needs_input_grad[4]
+    res = ift_gradient(z, J, D, S, ext, R, grad_R, solver=ctx.solver, return_mu=True, return_grad_ext=need_ext)
+    dJ, dD, dS = res[:3]
+    last_adjoint['status'], last_adjoint['iters'] = res[4], res[5]
+    g_ext = None
+    if need_ext:
+        g_ext = res[6] if ext.dim() == 3 else res[6].sum(dim=0)
+        g_ext = g_ext.to(ext.dtype)
+    return (None, dJ.to(J.dtype).to(J.device), dD.to(D.dtype).to(D.device), dS.to(S.dtype).to(S.device), g_ext)
+
+
 class SSNFixedPoint(torch.autograd.Function):
     """R = fixed_point(W(z; J, D, S), ext); backward = implicit gradient w.r.t. J, D, S."""
 
@@ -111,15 +150,29 @@ class SSNFixedPoint(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_R, _gs, _gi):
         z, J, D, S, ext, R = ctx.saved_tensors
-        need_ext = ctx.needs_input_grad[4]
-        res = ift_gradient(z, J, D, S, ext, R, grad_R, solver=ctx.solver, return_grad_ext=need_ext)
-        dJ, dD, dS = res[:3]
-        g_ext = None
-        if need_ext:
-            g_ext = res[3] if ext.dim() == 3 else res[3].sum(dim=0)
-            g_ext = g_ext.to(ext.dtype)
-        return (None, dJ.to(J.dtype).to(J.device), dD.to(D.dtype).to(D.device), dS.to(S.dtype).to(S.device),
-                g_ext, None, None)
+        return _ift_backward(ctx, z, J, D, S, ext, R, grad_R) + (None, None)
+
+
+class SSNAttachFixedPoint(torch.autograd.Function):
+    """Identity on fixed points R that were solved beforehand (e.g. by a rejection-sampling loop run without
+    autograd): puts them into the graph so that backward is the implicit gradient w.r.t. J, D, S (and ext).
+    The implicit-function theorem needs only the fixed point itself, not the path that led to it."""
+
+    @staticmethod
+    def forward(ctx, z, J, D, S, ext, R, solver):
+        ctx.save_for_backward(z, J, D, S, ext, R)
+        ctx.solver = solver
+        return R.clone()
+
+    @staticmethod
+    def backward(ctx, grad_R):
+        z, J, D, S, ext, R = ctx.saved_tensors
+        return _ift_backward(ctx, z, J, D, S, ext, R, grad_R) + (None, None)
+
+
+def attach_fixed_point(z, J, D, S, ext, R, solver=None):
+    """Differentiable view of already-solved fixed points `R` of the networks `z` (see SSNAttachFixedPoint)."""
+    return SSNAttachFixedPoint.apply(z, J, D, S, ext, R.detach(), solver or make_solver())
 
 
 def ssn_fixed_point(z, J, D, S, ext, solver=None, precise=False):
@@ -153,8 +206,11 @@ class EulerSSN(torch.autograd.Function):
     """(time_avg, dynamics_penalty, rate_penalty) of the unrolled Euler SSN; BPTT backward."""
 
     @staticmethod
-    def forward(ctx, z, J, D, S, ext, seqlen, skip_steps, solver, threshold):
-        need_grad = any(ctx.needs_input_grad[1:5])
+    def forward(ctx, z, J, D, S, ext, seqlen, skip_steps, solver, threshold, grad_enabled):
+        # needs_input_grad only mirrors requires_grad; under torch.no_grad() (critic updates) nothing will ever
+        # call backward, and storing the trajectory (2 x nz*seqlen*nb*2N floats) would be pure waste.  Grad mode
+        # is always off inside Function.forward, so the caller passes it in.
+        need_grad = grad_enabled and any(ctx.needs_input_grad[1:5])
         time_avg, pen, traj, gain = euler_forward(z, J, D, S, ext, seqlen, skip_steps, solver, threshold,
                                                   store=need_grad)
         nz, nb, dim = time_avg.shape
@@ -175,22 +231,28 @@ class EulerSSN(torch.autograd.Function):
         nz, _, nb, dim = traj.shape
         dev = traj.device
         g32 = _f32c(g_avg) if g_avg is not None else torch.zeros((nz, nb, dim), dtype=torch.float32, device=dev)
-        w_dyn = float(g_dyn) / n_dyn if g_dyn is not None else 0.0
-        w_rate = float(g_rate) / n_rate if g_rate is not None else 0.0
+        # the upstream scalar gradients stay on the device (no float(): that would drain the stream)
+        w_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        if g_dyn is not None:
+            w_dev[0] = g_dyn
+        if g_rate is not None:
+            w_dev[1] = g_rate
+        w_dyn, w_rate = 1.0 / n_dyn, 1.0 / n_rate
         adj = torch.empty_like(traj)
         grad = torch.empty(12, dtype=torch.float64, device=dev)
         gext = torch.zeros((nz, nb, dim), dtype=torch.float32, device=dev) if need_ext else None
         with torch.cuda.device(dev):
             clib.check_call(libssnode.ssn_euler_backward(
                 solver, nz, nb, dim // 2, _f32c(z).data_ptr(), _jds_struct(J, D, S), int(seqlen), int(skip_steps),
-                float(threshold), g32.data_ptr(), w_dyn, w_rate, traj.data_ptr(), gain.data_ptr(), adj.data_ptr(),
+                float(threshold), g32.data_ptr(), w_dyn, w_rate, w_dev.data_ptr(), traj.data_ptr(), gain.data_ptr(),
+                adj.data_ptr(),
                 grad.data_ptr(), None if gext is None else gext.data_ptr(), _stream()), 'ssn_euler_backward')
         dJ, dD, dS = grad[0:4].reshape(2, 2), grad[4:8].reshape(2, 2), grad[8:12].reshape(2, 2)
         g_ext = None
         if need_ext:
             g_ext = (gext if ext_dim == 3 else gext.sum(dim=0)).to(ext_dtype)
         return (None, dJ.to(J.dtype).to(J.device), dD.to(D.dtype).to(D.device), dS.to(S.dtype).to(S.device),
-                g_ext, None, None, None, None)
+                g_ext, None, None, None, None, None)
 
 
 def euler_ssn(z, J, D, S, ext, seqlen=1200, skip_steps=1000, dt=0.1, tau_E=10.0, tau_I=1.0,
@@ -205,7 +267,48 @@ def euler_ssn(z, J, D, S, ext, seqlen=1200, skip_steps=1000, dt=0.1, tau_E=10.0,
     solver = clib.make_solver(io_type=io_type, k=k, n=n, tau=(tau_E, tau_I), dt=dt,
                               rate_soft_bound=rate_soft_bound, rate_hard_bound=rate_hard_bound,
                               rate_stop_at=rate_hard_bound)
-    return EulerSSN.apply(z, J, D, S, ext, int(seqlen), int(skip_steps), solver, float(rate_penalty_threshold))
+    return EulerSSN.apply(z, J, D, S, ext, int(seqlen), int(skip_steps), solver, float(rate_penalty_threshold),
+                          torch.is_grad_enabled())
+
+
+class ProbeRates(torch.autograd.Function):
+    """tuning_curve[i, b] = rates[model_ids[i], b, probes[i]] (tc_gan/networks/cwgan.py:96-99); backward is the
+    scatter-add into dL/d rates that the BPTT / implicit-gradient kernels consume."""
+
+    @staticmethod
+    def forward(ctx, rates, model_ids, probes):
+        _check_cuda(rates, model_ids, probes)
+        r32 = _f32c(rates)
+        nz, nb, dim = r32.shape
+        ids = model_ids.to(torch.int32).contiguous()
+        prb = probes.to(torch.int32).contiguous()
+        batch = ids.numel()
+        assert prb.numel() == batch
+        out = torch.empty((batch, nb), dtype=torch.float32, device=rates.device)
+        with torch.cuda.device(rates.device):
+            clib.check_call(libssnode.ssn_probe_gather(r32.data_ptr(), ids.data_ptr(), prb.data_ptr(), batch, nz, nb,
+                                                       dim // 2, out.data_ptr(), _stream()), 'ssn_probe_gather')
+        ctx.save_for_backward(ids, prb)
+        ctx.shape = (nz, nb, dim)
+        ctx.dtype = rates.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ids, prb = ctx.saved_tensors
+        nz, nb, dim = ctx.shape
+        g = _f32c(grad_out)
+        grad_rates = torch.empty((nz, nb, dim), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            clib.check_call(libssnode.ssn_probe_scatter(g.data_ptr(), ids.data_ptr(), prb.data_ptr(), ids.numel(), nz,
+                                                        nb, dim // 2, grad_rates.data_ptr(), _stream()),
+                            'ssn_probe_scatter')
+        return grad_rates.to(ctx.dtype), None, None
+
+
+def probe_rates(rates, model_ids, probes):
+    """Differentiable gather of one probed neuron per batch element: [batch, nb] from rates [nz, nb, 2N]."""
+    return ProbeRates.apply(rates, model_ids, probes)
 
 
 def hetero_input(ext, zs_in, V):

@@ -205,6 +205,39 @@ def test_fifty_stimuli_sixteen_networks(ssn, oracle):
     check_sweeps(its, it_o)
 
 
+def test_find_fixed_points_streamed_variants(ssn, oracle):
+    """The streamed pointer-list entry point behind find_fixed_points: float64 W per network (the reference's
+    calling convention, run/gan.py:622-634), the z-based variant (jds=..., W built on the GPU, float64 or float32
+    z), more networks than one staging slab, a non-zero r0, and `info.solutions` behaving like the reference's."""
+    n_sites, nz = 40, 70
+    jds = oracle.new_JDS()
+    zs, W, exts = seeded_problem(oracle, n_sites, nz, seed=77)
+    Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
+    assert (st_o == 0).all()
+    kw = dict(k=0.01, n=2.2, r0=np.zeros(2 * n_sites))
+    Zs, Rs, info = ssn.find_fixed_points(nz, ((zs[i], W[i]) for i in range(nz)), exts, **kw)
+    np.testing.assert_array_equal(Zs, zs)
+    np.testing.assert_allclose(Rs, Ro, rtol=RTOL, atol=ATOL)
+    assert len(info.solutions) == nz and len(info.solutions[3]) == len(exts)
+    assert all(s.success and s.message == 'Converged' for s in info.solutions[-1])
+    np.testing.assert_array_equal(info.solutions[5][2].x, Rs[5, 2])
+    assert info.solutions[5][2].iterations == it_o[5, 2] or abs(info.solutions[5][2].iterations - it_o[5, 2]) <= 1
+    for ztype in (np.float64, np.float32):
+        z_in = zs.astype(ztype)
+        Wz = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z_in.astype(np.float64))
+        Rz_o, _, _ = oracle.fixed_point_batch(Wz, exts, threads=8)
+        Zs2, Rs2, _ = ssn.find_fixed_points(nz, ((z_in[i], None) for i in range(nz)), exts, jds=jds, host_threads=3, **kw)
+        assert Zs2.dtype == ztype
+        np.testing.assert_allclose(Rs2, Rz_o, rtol=RTOL, atol=ATOL)
+    r0 = np.full(2 * n_sites, 2.5)
+    x, code, _ = oracle.fixed_point(W[1], exts[6], r0=r0)
+    _, Rs3, _ = ssn.find_fixed_points(3, ((zs[i], W[i]) for i in range(3)), exts, k=0.01, n=2.2, r0=r0)
+    np.testing.assert_allclose(Rs3[1, 6], x, rtol=RTOL, atol=ATOL)
+    # the float64 kernel through the same API
+    _, Rs4, _ = ssn.find_fixed_points(4, ((zs[i], W[i]) for i in range(4)), exts, precise=True, **kw)
+    np.testing.assert_allclose(Rs4, Ro[:4], rtol=0, atol=1e-10)
+
+
 def test_initial_state_and_max_iter(ssn, oracle):
     n_sites = 20
     _, W, exts = seeded_problem(oracle, n_sites, 2, seed=1)
@@ -265,23 +298,6 @@ def test_tight_atol_on_the_fast_path(ssn, oracle):
     assert (err == 0).all() and (st_o == 0).all()
     np.testing.assert_allclose(R, Ro, rtol=1e-6, atol=1e-6)
     assert np.abs(its - it_o).max() <= 2
-
-
-def test_lockstep_register_kernel(ssn, oracle):
-    """The register-resident kernel without warp specialisation (SSN_K1=regw; the path taken when the
-    warp-specialised kernel cannot be planned) meets the same bar as the default kernel."""
-    os.environ['SSN_K1'] = 'regw'
-    try:
-        for n_sites, nz, nb in ((33, 3, 8), (101, 2, 9), (201, 2, 8)):
-            bw = np.linspace(0, 1, nb)
-            _, W, exts = seeded_problem(oracle, n_sites, nz, seed=20 + n_sites, bandwidths=bw)
-            Ro, st_o, it_o = oracle.fixed_point_batch(W, exts, threads=8)
-            R, err, its = ssn.fixed_points_batch(W, exts, k=0.01, n=2.2)
-            np.testing.assert_array_equal(err, st_o)
-            np.testing.assert_allclose(R, Ro, rtol=RTOL, atol=ATOL)
-            check_sweeps(its, it_o)
-    finally:
-        del os.environ['SSN_K1']
 
 
 def test_reference_abi_from_a_thread_pool(ssn, oracle):

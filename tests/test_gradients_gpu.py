@@ -218,3 +218,58 @@ def test_heterogeneous_input_gradients(ops, oracle):
             mu = np.linalg.solve(np.eye(2 * n_sites) - W[iz].T * phi[None, :], G[iz, ib])
             dV += np.sum(phi * mu * zs_in[iz] * exts[ib])           # dL/d ext * d ext/dV
     assert abs(float(Vs.grad) - dV) <= 2e-4 * abs(dV), (float(Vs.grad), dV)
+
+
+def test_rejected_network_does_not_poison_the_implicit_gradient(ops, oracle):
+    """A network masked out by the caller (dL/dr = 0) whose state is non-finite -- e.g. a diverged asym_power solve --
+    must contribute exactly nothing: the 12 accumulators equal those of the batch without it, and the adjoint
+    status of its solves is 0 with 0 sweeps."""
+    import torch
+    n_sites, nz, nb = 30, 3, 8
+    jds = oracle.new_JDS()
+    exts = oracle.stimulus_input(oracle.DEFAULT_BANDWIDTHS, n_sites)
+    rs = np.random.RandomState(3)
+    z = rs.rand(nz, 2 * n_sites, 2 * n_sites).astype(np.float32).astype(np.float64)
+    W = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
+    R, st, _ = oracle.fixed_point_batch(W, exts)
+    assert (st == 0).all()
+    gR = rs.randn(nz, nb, 2 * n_sites)
+    gR[1] = 0.0
+    R_bad = R.copy()
+    R_bad[1] = np.nan
+    R_bad[1, 3] = np.inf
+    solver = ops.make_solver()
+    J, D, S = (tens(jds[k], torch.float64) for k in 'JDS')
+    keep = [0, 2]
+    want = ops.ift_gradient(tens(z[keep]), J, D, S, tens(exts), tens(R[keep]), tens(gR[keep]), solver=solver)
+    got = ops.ift_gradient(tens(z), J, D, S, tens(exts), tens(R_bad), tens(gR), solver=solver, return_mu=True)
+    for a, b in zip(got[:3], want[:3]):
+        assert torch.isfinite(a).all()
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-9, atol=1e-9 * float(b.abs().max()))
+    mu, status, iters = got[3:6]
+    assert (status.cpu().numpy() == 0).all() and (iters[1].cpu().numpy() == 0).all()
+    assert (mu[1] == 0).all()
+
+
+def test_no_grad_forward_stores_no_trajectory(ops, monkeypatch):
+    """Critic updates run the generator under torch.no_grad(): J, D, S still have requires_grad, but the forward
+    must not store the trajectory and gain arrays (2 x nz * seqlen * nb * 2N floats) that only backward reads."""
+    import torch
+    from tc_gan_b200 import ssnode
+    seen = []
+    real = ops.euler_forward
+
+    def spy(*args, **kwargs):
+        seen.append(kwargs.get('store'))
+        return real(*args, **kwargs)
+
+    monkeypatch.setattr(ops, 'euler_forward', spy)
+    jds = ssnode.new_JDS()
+    J, D, S = (tens(jds[k], torch.float64, grad=True) for k in 'JDS')
+    z = tens(np.random.RandomState(0).rand(2, 20, 20))
+    ext = tens(np.random.RandomState(1).rand(3, 20))
+    with torch.no_grad():
+        avg, _, _ = ops.euler_ssn(z, J, D, S, ext, seqlen=20, skip_steps=10)
+    avg2, _, _ = ops.euler_ssn(z, J, D, S, ext, seqlen=20, skip_steps=10)
+    assert seen == [False, True] and not avg.requires_grad and avg2.requires_grad
+    torch.testing.assert_close(avg, avg2.detach())
