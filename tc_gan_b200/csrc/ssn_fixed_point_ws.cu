@@ -6,7 +6,7 @@
 //   * CW CONTRACTION warps hold the W tile (TI rows x NC columns per thread: warp w owns rows w*TI.., lane l the
 //     columns l, l+32, ...; rows packed in pairs for FFMA2) and do nothing but  wait panel -> FFMA2 contraction ->
 //     32-lane reduce-scatter -> hand one dv per lane to their update warp through shared memory;
-//   * UW UPDATE warps (warp u serves the G = CW / UW contraction warps u*G .. u*G+G-1; lane = 4 * row + stimulus
+//   * UW UPDATE warps (warp u serves the G = CW / UW contraction warps u, u+UW, ..: the ones on its own scheduler; lane = 4 * row + stimulus
 //     slot owns one output per served warp and stream) own the float64 state, evaluate f from the tables, apply
 //     the Euler step and the stopping tests, and publish the new r - r_ref (and the warp's flag word) to every CTA
 //     of the cluster with st.async remote stores that complete bytes on the destination's mbarrier;
@@ -17,10 +17,11 @@
 //     the next half-panel of the network (nb > 8), so both streams stay busy until the network runs out of
 //     stimuli; only then does the last stream run alone.
 //
-// Shapes.  <CW, UW, TI> = <12, 4, 6>: 72 rows per CTA, so 2N = 402 takes a cluster of 6 (22 resident clusters =
-// 132 SMs on a B200; clusters of 8 only fit 15 times = 120 SMs), three contraction warps per scheduler, 78 W
-// registers per thread.  <8, 8, 7>: 56 rows per CTA (cluster of 8 at 2N = 402), the round-1 shape, kept for
-// sizes where its smaller tile pads less.  The plan picks by padded work per SM (SSN_WS_SHAPE overrides).
+// Shapes.  The kernel is generic in <CW, UW, TI>.  Production shape <8, 8, 7>: 56 rows per CTA, a cluster of 8
+// at 2N = 402 (15 resident clusters = 120 SMs on a B200), one update warp per contraction warp.  The wider
+// <12, 4, 6> (72 rows per CTA: clusters of 6, 22 resident = 132 SMs, three contraction warps per scheduler) is
+// compiled only with -DSSN_WS_SHAPE_B: measured 96 k solves/s against 111 k -- its four update warps carry three
+// outputs per lane and become the bottleneck of every sweep.
 //
 // Numerics -- reference-point iteration.  Per stimulus the kernel iterates on r - r_ref:
 // v = v_ref + W fl32(r - r_ref) (FP32 FFMA2), f(v) in float64 from cubic Taylor tables in shared memory,
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
 #endif
     } else {
         // =====================================================================================
-        // update warps: warp u serves contraction warps u*G .. u*G+G-1; lane = 4 * row + stimulus slot owns one
+        // update warps: warp u serves contraction warps u, u + UW, .. (same scheduler); lane = 4 * row + stimulus slot owns one
         // output per served warp and stream
         // =====================================================================================
         reg_release<SH::REG_U>();
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
         unsigned xoff[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const int lrow = (u * G + g) * TI + my_t;                           // local row
+            const int lrow = ((u + g * UW)) * TI + my_t;                           // local row
             grow[g] = row_base + lrow;
             owner[g] = my_t < TI && lrow < rows_here;
             xoff[g] = 16u * (unsigned)grow[g] + 4u * (unsigned)my_b;            // slot of the global row
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
         // r_ref and v_ref of the owned outputs live in shared memory (they change only at refresh events and are
         // read once per sweep), r in registers
         auto ref_slot = [&](int h, int which, int g) -> double & {
-            return refbuf[((h * 2 + which) * CW + u * G + g) * 32 + lane];
+            return refbuf[((h * 2 + which) * CW + (u + g * UW)) * 32 + lane];
         };
         // Publish: lanes 0..4*TI-1 send the new r - r_ref of their outputs, lane 28 the warp's flag word, to the
         // same panel offset in every CTA of the cluster: a plain store at home, st.async (remote store that
@@ -670,7 +671,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
 #pragma unroll
                             for (int g = 0; g < G; ++g) {
                                 if (!owner[g]) continue;
-                                ref_slot(h, 1, g) = exbuf[(h * CW + u * G + g) * 32 + lane] + (double)sext[h][g];
+                                ref_slot(h, 1, g) = exbuf[(h * CW + (u + g * UW)) * 32 + lane] + (double)sext[h][g];
                                 ref_slot(h, 0, g) = sr[h][g];
                             }
                             if ((natural >> st) & 1u) levels += 1u << (4 * h);      // next rung of the ladder
@@ -687,10 +688,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                     const unsigned dvpar = (dvph >> h) & 1u;
                     // all served contraction warps first: the G updates below are independent chains and interleave
 #pragma unroll
-                    for (int g = 0; g < G; ++g) mbar_wait(smem_u32(&misc->dvfull[h][u * G + g]), dvpar);
+                    for (int g = 0; g < G; ++g) mbar_wait(smem_u32(&misc->dvfull[h][(u + g * UW)]), dvpar);
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        const float dv = dvbuf[(h * CW + u * G + g) * 32 + lane];
+                        const float dv = dvbuf[(h * CW + (u + g * UW)) * 32 + lane];
                         const bool lv = owner[g] && slot_live;
                         const double vv = ref_slot(h, 1, g) + (double)dv;
                         bool rare;
@@ -752,7 +753,9 @@ typedef void (*WsKernel)(const RwArgs);
 #define SSN_WS_RC_A 184
 #endif
 using ShapeA = WsShape<8, 8, 7, SSN_WS_RC_A, SSN_WS_PF_A>;             // 56 rows per CTA
-using ShapeB = WsShape<12, 4, 6, SSN_WS_RC_B, SSN_WS_PF_B>;    // 72 rows per CTA
+#ifdef SSN_WS_SHAPE_B
+using ShapeB = WsShape<12, 4, 6, SSN_WS_RC_B, SSN_WS_PF_B>;    // 72 rows per CTA (experiment, see the header)
+#endif
 
 struct WsPlan { WsKernel fn; int shape, nc, kpad, csize, rpc, smem, clusters, tab_nodes, cw, uw, ti; };
 
@@ -817,24 +820,12 @@ static int plan_ws_shape(const ssn_solver &sv, int n_sites, int nz, int shape_id
     return 0;
 }
 
-// Shape choice: the one whose resident clusters carry the most useful rows per sweep time.  A sweep costs a CTA
-// about (FMA issue of its warps on the busiest scheduler) + a fixed exchange / reduce overhead, so the figure of
-// merit is  resident clusters x dim rows  /  (warps per scheduler x TI x NC + overhead);  SSN_WS_SHAPE=A|B forces.
 static int plan_ws(const ssn_solver &sv, int n_sites, int nz, WsPlan *plan) {
+#ifdef SSN_WS_SHAPE_B
     const char *force = getenv("SSN_WS_SHAPE");
-    WsPlan pa, pb;
-    const int ra = (force && (force[0] == 'B' || force[0] == 'b')) ? 1 : plan_ws_shape<ShapeA>(sv, n_sites, 0, 0, &pa);
-    const int rb = (force && (force[0] == 'A' || force[0] == 'a')) ? 1 : plan_ws_shape<ShapeB>(sv, n_sites, 0, 1, &pb);
-    if (ra > 1 || ra < 0) return ra;
-    if (rb > 1 || rb < 0) return rb;
-    if (ra && rb) return 1;
-    auto merit = [](const WsPlan &p) {
-        const double step = (p.cw / 4.0) * p.ti * p.nc * 2.0 + 900.0;      // cycles per stream step, rough
-        return p.clusters / step;
-    };
-    *plan = ra ? pb : rb ? pa : (merit(pb) >= merit(pa) ? pb : pa);
-    if (nz > 0) plan->clusters = std::min(plan->clusters, nz);
-    return 0;
+    if (force && (force[0] == 'B' || force[0] == 'b')) return plan_ws_shape<ShapeB>(sv, n_sites, nz, 1, plan);
+#endif
+    return plan_ws_shape<ShapeA>(sv, n_sites, nz, 0, plan);
 }
 
 int ws_occupancy(const ssn_solver &sv, int n_sites, int *cluster_size, int *resident_clusters) {
