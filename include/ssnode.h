@@ -166,8 +166,10 @@ SSN_API int ssn_ift_gradient_batch(const ssn_solver *solver, int nz, int nb, int
  *   time_avg   float32 [nz][nb][2N]
  *   penalties  float64 [2]: sum (r_{t+1}-r_t)^2 and sum relu(r_t - threshold)
  *              (un-normalised sums; the caller divides by the element counts)
- *   traj       float32 [nz][seqlen][nb][2N] or NULL: states r_1..r_seqlen
- *   gain       float32 [nz][seqlen][nb][2N] or NULL: eps*f'(W r_t + I), t = 0..seqlen-1
+ *   traj       float32 [nz][seqlen][nb][pitch] or NULL: states r_1..r_seqlen
+ *   gain       float32 [nz][seqlen][nb][pitch] or NULL: eps*f'(W r_t + I), t = 0..seqlen-1
+ *              (pitch = ssn_traj_pitch(n_sites) = 2N rounded up to a multiple of 4 floats: 16-byte rows, which
+ *              the TMA loads of the backward pass need; the pad columns are never read)
  * eps_E = dt/tau_E, eps_I = dt/tau_I from `solver`.  Device pointers only.
  */
 SSN_API int ssn_euler_forward(const ssn_solver *solver, int nz, int nb, int n_sites,
@@ -181,7 +183,9 @@ SSN_API int ssn_euler_forward(const ssn_solver *solver, int nz, int nb, int n_si
  * BPTT through ssn_euler_forward: given dL/d time_avg [nz][nb][2N] and the
  * scalar weights dL/d(dynamics sum), dL/d(rate sum), returns dL/dJ, dL/dD,
  * dL/dS in grad[12] (float64, device, zeroed here).  `traj` and `gain` are the
- * arrays the forward call stored; `adj` is scratch of the same size as traj.
+ * arrays the forward call stored; `adj` is scratch of the same size as traj (all three with rows of
+ * ssn_traj_pitch(n_sites) floats).  The parameter-gradient contraction sum_k adj_k traj_k^T runs on the
+ * tensor cores (tcgen05 kind::tf32 with a 3-term split, TMA operand loads).
  * grad_ext (float32 [nz][nb][2N], may be NULL) receives dL/d ext = sum_t gain[t] * lambda_{t+1}.
  * w_dev (device float32 [2], may be NULL): when given, the kernel multiplies w_dyn and w_rate by w_dev[0] and
  * w_dev[1] read on the device, so that upstream scalar gradients need no device-to-host copy.
@@ -192,6 +196,11 @@ SSN_API int ssn_euler_backward(const ssn_solver *solver, int nz, int nb, int n_s
                        const float *grad_time_avg, double w_dyn, double w_rate, const float *w_dev,
                        const float *traj, const float *gain, float *adj,
                        double *grad, float *grad_ext, void *stream);
+
+/* The parameter-gradient contraction of ssn_euler_backward alone: grad[12] (device float64, zeroed here) =
+ * < sum_k adj_k traj_k^T, dW/d(J, D, S) > over k = (t, b); adj, traj [nz][seqlen][nb][pitch] device float32. */
+SSN_API int ssn_bptt_param_grad(int nz, int nb, int n_sites, int seqlen, const float *adj, const float *traj,
+                        const float *z, const ssn_jds *jds, double *grad, void *stream);
 
 /*
  * Probes: tuning_curve[i][b] = rates[model_ids[i]][b][probes[i]] for i < batch -- the gather of
@@ -215,6 +224,9 @@ SSN_API const char *ssn_last_error(void);           /* thread-local text of the 
 SSN_API int ssn_kernel_launches(void);              /* kernels launched by this library so far (process-wide) */
 /* clusters the fixed-point kernel keeps resident for a given size, and its cluster width */
 SSN_API int ssn_fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters);
+
+/* floats per row of the BPTT scratch arrays (traj, gain, adj): 2N rounded up to a multiple of 4 */
+SSN_API int ssn_traj_pitch(int n_sites);
 
 /* shape tag of the kernel the FP32 path runs for this size, e.g. "ssn_fp_ws_kernel<NC=14,CW=8,UW=8,TI=7>x8"
  * (kernel<template shape> x cluster width): keys the committed ncu figures in profiles/ */

@@ -144,6 +144,11 @@ libssnode.ssn_kernel_launches.restype = c_int
 libssnode.ssn_fixed_point_occupancy.argtypes = [c_int, int_ptr, int_ptr]
 libssnode.ssn_fixed_point_occupancy.restype = c_int
 
+libssnode.ssn_bptt_param_grad.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, POINTER(JDSStruct),
+                                          c_void_p, c_void_p]
+libssnode.ssn_bptt_param_grad.restype = c_int
+libssnode.ssn_traj_pitch.argtypes = [c_int]
+libssnode.ssn_traj_pitch.restype = c_int
 libssnode.ssn_fixed_point_kernel_name.argtypes = [c_int, ctypes.c_char_p, c_int]
 libssnode.ssn_fixed_point_kernel_name.restype = c_int
 libssnode.ssn_profile_enable.argtypes = [c_int]
@@ -160,7 +165,7 @@ EXPORTED_SYMBOLS = (
     'ssn_fixed_point_batch', 'ssn_fixed_point_batch_f64', 'ssn_ift_gradient_batch',
     'ssn_euler_forward', 'ssn_euler_backward', 'ssn_generate_weight', 'ssn_device_count',
     'ssn_last_error', 'ssn_kernel_launches', 'ssn_fixed_point_occupancy',
-    'ssn_measure_fp32_peak', 'ssn_profile_enable', 'ssn_profile_read', 'ssn_probe_gather', 'ssn_probe_scatter', 'ssn_fixed_point_batch_ptrs', 'ssn_host_gather', 'ssn_fixed_point_kernel_name')
+    'ssn_measure_fp32_peak', 'ssn_profile_enable', 'ssn_profile_read', 'ssn_probe_gather', 'ssn_probe_scatter', 'ssn_fixed_point_batch_ptrs', 'ssn_host_gather', 'ssn_fixed_point_kernel_name', 'ssn_traj_pitch', 'ssn_bptt_param_grad')
 
 
 class SSNLibraryError(RuntimeError):

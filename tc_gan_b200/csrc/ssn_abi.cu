@@ -760,6 +760,16 @@ int ssn_euler_backward(const ssn_solver *solver, int nz, int nb, int n_sites, co
                                  (cudaStream_t)stream);
 }
 
+// The parameter-gradient contraction alone (development / tests): grad[12] = < sum_k adj_k traj_k^T, dW/dtheta >.
+int ssn_bptt_param_grad(int nz, int nb, int n_sites, int seqlen, const float *adj, const float *traj, const float *z,
+                        const ssn_jds *jds, double *grad, void *stream) {
+    if (!adj || !traj || !z || !jds || !grad || nz < 0 || nb < 1 || seqlen < 1 || n_sites < 1) {
+        set_error("ssn_bptt_param_grad: bad arguments");
+        return -1;
+    }
+    return launch_bptt_param_grad(nz, nb, n_sites, seqlen, adj, traj, z, *jds, grad, (cudaStream_t)stream);
+}
+
 // ---- probes (output-side boundary) ---------------------------------------------------------
 int ssn_probe_gather(const float *rates, const int *model_ids, const int *probes, int batch, int nz, int nb,
                      int n_sites, float *out, void *stream) {
@@ -789,6 +799,7 @@ int ssn_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed
 int ssn_fixed_point_occupancy(int n_sites, int *cluster_size, int *resident_clusters) {
     return fixed_point_occupancy(n_sites, cluster_size, resident_clusters);
 }
+int ssn_traj_pitch(int n_sites) { return traj_pitch(n_sites); }
 int ssn_fixed_point_kernel_name(int n_sites, char *buf, int cap) {
     return fixed_point_kernel_name(n_sites, buf, cap);
 }

@@ -13,6 +13,8 @@
 //
 // Forward and the adjoint recursion run on the cluster-resident machinery of K1/K2
 // (W, then W^T, in distributed shared memory; one DSMEM exchange per time step).
+#include <cstdlib>
+#include <cstring>
 #include "ssn_cluster_core.cuh"
 #include "ssn_launch.h"
 
@@ -28,6 +30,7 @@ struct EulerArgs {
     const float *ext;
     long long ext_stride_z;
     int seqlen, skip;
+    int pitch;                          // floats per (time step, stimulus) row of traj / gain / adj: 2N rounded up to 4
     float threshold;
     int *work_counter;
     IoConst<float> io;
@@ -115,22 +118,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
 
             unsigned xoff[TO];
             double eps_own[TO], state[TO];             // r_k (forward) or lambda_{k+1} (backward)
-            size_t goff[TO];                           // offset of (stim, row) inside one time slice
+            size_t goff[TO];                           // offset of (stim, row) inside one [nb][2N] slice
+            size_t toff[TO];                           // ... inside one [nb][pitch] time slice of traj / gain / adj
 #pragma unroll
             for (int u = 0; u < TO; ++u) {
-                xoff[u] = 0u; eps_own[u] = 0.0; state[u] = 0.0; goff[u] = 0;
+                xoff[u] = 0u; eps_own[u] = 0.0; state[u] = 0.0; goff[u] = 0; toff[u] = 0;
                 if (valid[u]) {
                     const int gr = row_base + own0 + u;
                     xoff[u] = 4u * (unsigned)panel_index(P, 0, gr, my_stim);
                     eps_own[u] = gr < N ? a.eps_E : a.eps_I;
                     goff[u] = (size_t)stim_g * dim + gr;
+                    toff[u] = (size_t)stim_g * a.pitch + gr;
 #pragma unroll
                     for (int p = 0; p < MAX_CLUSTER; ++p)
                         if (p < csize) st_cluster_f32(xpeer[p] + xoff[u], 0.f);
                 }
             }
-            const size_t slice = (size_t)a.nb * dim;                    // one time step of one network
-            const size_t net_base = (size_t)net * seqlen * slice;
+            const size_t slice = (size_t)a.nb * dim;                    // one [nb][2N] array of one network
+            const size_t tslice = (size_t)a.nb * a.pitch;               // one time step of one network in traj / gain / adj
+            const size_t net_base = (size_t)net * seqlen * tslice;
 
             if (!BACKWARD) {
                 float ext_own[TO];
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                                     pen_rate += fmax(r_new - (double)a.threshold, 0.0);
                                     if (t > skip) pen_dyn += (r_new - r_old) * (r_new - r_old);
                                 }
-                                const size_t o = net_base + (size_t)t * slice + goff[u];
+                                const size_t o = net_base + (size_t)t * tslice + toff[u];
                                 if (a.traj) a.traj[o] = (float)r_new;
                                 if (a.gain)
                                     a.gain[o] = (float)eps_own[u] * (pw ? a.io.n * fv / vt : io_gain<float>(a.io, vt));
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                     gavg[u] = 0.f; r_cur[u] = 0.f; r_next[u] = 0.f; gext[u] = 0.f;
                     if (valid[u] && active) {
                         gavg[u] = __ldg(a.g_avg + (size_t)net * slice + goff[u]) / (float)T;
-                        r_cur[u] = __ldg(a.traj_in + net_base + (size_t)(seqlen - 1) * slice + goff[u]);
+                        r_cur[u] = __ldg(a.traj_in + net_base + (size_t)(seqlen - 1) * tslice + toff[u]);
                     }
                 }
                 cluster.sync();
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                             float r_prev = 0.f;
                             double lam = 0.0;
                             if (active) {
-                                if (tp > 0) r_prev = __ldg(a.traj_in + net_base + (size_t)(tp - 1) * slice + goff[u]);
+                                if (tp > 0) r_prev = __ldg(a.traj_in + net_base + (size_t)(tp - 1) * tslice + toff[u]);
                                 double d = 0.0;
                                 if (k >= skip + 1) {
                                     d = (double)gavg[u];
@@ -227,13 +233,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                             // q_{k-1} = gain[k-1] * lambda_k, paired with r_{k-1} = traj[tp-1]
                             float q = 0.f;
                             if (active) {
-                                q = __ldg(a.gain_in + net_base + (size_t)tp * slice + goff[u]) * (float)lam;
+                                q = __ldg(a.gain_in + net_base + (size_t)tp * tslice + toff[u]) * (float)lam;
                                 gext[u] += q;                             // dL/d ext = sum_k q_k, q_0 included
-                                if (tp > 0) a.adj[net_base + (size_t)(tp - 1) * slice + goff[u]] = q;
+                                if (tp > 0) a.adj[net_base + (size_t)(tp - 1) * tslice + toff[u]] = q;
                                 else q = 0.f;                             // q_0 pairs with r_0 = 0: nothing to publish
                             }
                             if (active && tp == seqlen - 1)
-                                a.adj[net_base + (size_t)tp * slice + goff[u]] = 0.f;   // q_seqlen = 0
+                                a.adj[net_base + (size_t)tp * tslice + toff[u]] = 0.f;   // q_seqlen = 0
                             r_next[u] = r_cur[u];
                             r_cur[u] = r_prev;
                             const unsigned off = xoff[u] + (nbuf ? buf_bytes : 0u);
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
 // ------------------------------------------------------------------------------------
 constexpr int GT = 128, GK = 8;          // 128 x 128 output tile per CTA, K chunks of 8, 8 x 8 outputs per thread
 
-__global__ void __launch_bounds__(256) ssn_bptt_param_grad_kernel(int n_sites, long long K, const float *adj,
+__global__ void __launch_bounds__(256) ssn_bptt_param_grad_kernel(int n_sites, int pitch, long long K, const float *adj,
                                                                   const float *traj, const float *z,
                                                                   WeightConst wc, double *grad) {
     // double-buffered K chunks: [2][GK][GT] for each operand (2 x 2 x 8 x 128 x 4 B = 16 KB)
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(256) ssn_bptt_param_grad_kernel(int n_sites, l
     const int net = blockIdx.x / (tiles * tiles);
     const int ti = (blockIdx.x / tiles) % tiles, tj = blockIdx.x % tiles;
     const int i0 = ti * gt, j0 = tj * gt;
-    const float *A = adj + (size_t)net * K * dim, *B = traj + (size_t)net * K * dim;
+    const float *A = adj + (size_t)net * K * pitch, *B = traj + (size_t)net * K * pitch;
     const int tid = threadIdx.x;
     const bool worker = tid < n1 * n1;                      // n1 x n1 threads, 8 x 8 outputs each
     const int tx = worker ? tid % n1 : 0, ty = worker ? tid / n1 : 0;   // rows ty*4 + {0..3, half..half+3}, cols likewise
@@ -305,8 +311,8 @@ __global__ void __launch_bounds__(256) ssn_bptt_param_grad_kernel(int n_sites, l
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int col = lc + 32 * m;
-            ra[m] = (k < K && col < gt && i0 + col < dim) ? __ldg(A + k * dim + i0 + col) : 0.f;
-            rb[m] = (k < K && col < gt && j0 + col < dim) ? __ldg(B + k * dim + j0 + col) : 0.f;
+            ra[m] = (k < K && col < gt && i0 + col < dim) ? __ldg(A + k * pitch + i0 + col) : 0.f;
+            rb[m] = (k < K && col < gt && j0 + col < dim) ? __ldg(B + k * pitch + j0 + col) : 0.f;
         }
     };
     auto stash = [&](int buf) {
@@ -429,11 +435,32 @@ static int launch_euler(bool backward, EulerArgs &a, int n_sites, int nz, int *c
     return 0;
 }
 
+// dL/dtheta contraction (accumulates into grad): tcgen05 (TF32 x 3, TMA) by default, the FFMA kernel with SSN_K4B=ffma
+static int bptt_param_grad(int nz, int nb, int n_sites, int seqlen, const float *adj, const float *traj, const float *z,
+                           const WeightConst &wc, double *grad, cudaStream_t stream) {
+    const int pitch = traj_pitch(n_sites);
+    const char *k4b = getenv("SSN_K4B");
+    if (!(k4b && !strcmp(k4b, "ffma"))) {
+        const int rc = launch_bptt_param_grad_tc(nz, n_sites, (long long)seqlen * nb, pitch, adj, traj, z, wc, grad, stream);
+        if (rc != 1) return rc;                                   // 1: tensor maps unavailable -> FFMA kernel
+    }
+    const int dim = 2 * n_sites, tiles = (dim + GT - 1) / GT;
+    {
+        KernelTimer kt("ssn_bptt_param_grad_kernel", stream);
+        ssn_bptt_param_grad_kernel<<<nz * tiles * tiles, 256, 0, stream>>>(
+            n_sites, pitch, (long long)seqlen * nb, adj, traj, z, wc, grad);
+        SSN_CUDA(cudaGetLastError());
+    }
+    count_launch();
+    return 0;
+}
+
 static void fill_common(EulerArgs &a, const ssn_solver &sv, int nz, int nb, int n_sites, const float *z,
                         const ssn_jds &jds, int seqlen, int skip, double threshold) {
     a.nz = nz; a.nb = nb; a.n_sites = n_sites;
     a.z = z; a.wc = make_weight_const(jds, n_sites);
     a.seqlen = seqlen; a.skip = skip; a.threshold = (float)threshold;
+    a.pitch = traj_pitch(n_sites);
     a.io = make_io_const<float>(sv.io_type, sv.k, sv.n, sv.rate_soft_bound, sv.rate_hard_bound);
     a.eps_E = sv.dt / sv.tau_E; a.eps_I = sv.dt / sv.tau_I;
 }
@@ -463,15 +490,14 @@ int launch_euler_backward(const ssn_solver &sv, int nz, int nb, int n_sites, con
     a.traj_in = traj; a.gain_in = gain; a.adj = adj; a.grad_ext = grad_ext;
     int rc = launch_euler(true, a, n_sites, nz, counter, stream);
     if (rc) return rc;
-    const int dim = 2 * n_sites, tiles = (dim + GT - 1) / GT;
-    {
-        KernelTimer kt("ssn_bptt_param_grad_kernel", stream);
-        ssn_bptt_param_grad_kernel<<<nz * tiles * tiles, 256, 0, stream>>>(
-            n_sites, (long long)seqlen * nb, adj, traj, z, a.wc, grad);
-        SSN_CUDA(cudaGetLastError());
-    }
-    count_launch();
-    return 0;
+    return bptt_param_grad(nz, nb, n_sites, seqlen, adj, traj, z, a.wc, grad, stream);
+}
+
+int launch_bptt_param_grad(int nz, int nb, int n_sites, int seqlen, const float *adj, const float *traj, const float *z,
+                           const ssn_jds &jds, double *grad, cudaStream_t stream) {
+    SSN_CUDA(cudaMemsetAsync(grad, 0, 12 * sizeof(double), stream));
+    if (nz <= 0) return 0;
+    return bptt_param_grad(nz, nb, n_sites, seqlen, adj, traj, z, make_weight_const(jds, n_sites), grad, stream);
 }
 
 }  // namespace ssn

@@ -44,6 +44,18 @@ int launch_probe_gather(const float *rates, const int *model_ids, const int *pro
 int launch_probe_scatter(const float *grad_out, const int *model_ids, const int *probes, int batch, int nz, int nb,
                          int dim, float *grad_rates, cudaStream_t stream);
 
+// floats per (time step, stimulus) row of the BPTT scratch arrays traj / gain / adj: 2N rounded up to a multiple of 4,
+// so that rows are 16-byte aligned (TMA needs 16-byte global strides)
+inline int traj_pitch(int n_sites) { return (2 * n_sites + 3) & ~3; }
+// dL/dtheta = < sum_k adj_k traj_k^T, dW/dtheta > on the tensor cores (tcgen05 kind::tf32, 3-term split, TMA loads);
+// returns 1 when the driver cannot build tensor maps (the caller then uses the FFMA kernel)
+int launch_bptt_param_grad_tc(int nz, int n_sites, long long K, int pitch, const float *adj, const float *traj,
+                              const float *z, const WeightConst &wc, double *grad, cudaStream_t stream);
+
+// zeroes grad, then the contraction (tensor-core kernel, or the FFMA kernel with SSN_K4B=ffma)
+int launch_bptt_param_grad(int nz, int nb, int n_sites, int seqlen, const float *adj, const float *traj, const float *z,
+                           const ssn_jds &jds, double *grad, cudaStream_t stream);
+
 int launch_generate_weight(int nz, int n_sites, const float *z, const ssn_jds &jds, float *W, cudaStream_t stream);
 int launch_convert_f64_to_f32(const double *src, float *dst, size_t n, cudaStream_t stream);
 int launch_convert_f32_to_f64(const float *src, double *dst, size_t n, cudaStream_t stream);

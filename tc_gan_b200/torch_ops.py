@@ -191,8 +191,10 @@ def euler_forward(z, J, D, S, ext, seqlen, skip_steps, solver, rate_penalty_thre
     dev = z.device
     time_avg = torch.empty((nz, nb, dim), dtype=torch.float32, device=dev)
     pen = torch.zeros(2, dtype=torch.float64, device=dev)
-    traj = torch.empty((nz, seqlen, nb, dim), dtype=torch.float32, device=dev) if store else None
-    gain = torch.empty((nz, seqlen, nb, dim), dtype=torch.float32, device=dev) if store else None
+    # rows of the scratch arrays are padded to 16 bytes (ssn_traj_pitch): the backward pass loads them by TMA
+    pitch = int(libssnode.ssn_traj_pitch(dim // 2))
+    traj = torch.empty((nz, seqlen, nb, pitch), dtype=torch.float32, device=dev) if store else None
+    gain = torch.empty((nz, seqlen, nb, pitch), dtype=torch.float32, device=dev) if store else None
     with torch.cuda.device(dev):
         clib.check_call(libssnode.ssn_euler_forward(
             solver, nz, nb, dim // 2, z32.data_ptr(), _jds_struct(J, D, S), e32.data_ptr(), int(e32.dim() == 3),
@@ -228,7 +230,8 @@ class EulerSSN(torch.autograd.Function):
         z, J, D, S, traj, gain = ctx.saved_tensors
         seqlen, skip_steps, solver, threshold, n_dyn, n_rate, ext_dim, ext_dtype = ctx.meta
         need_ext = ctx.needs_input_grad[4]
-        nz, _, nb, dim = traj.shape
+        nz, _, nb, _pitch = traj.shape
+        dim = z.shape[1]
         dev = traj.device
         g32 = _f32c(g_avg) if g_avg is not None else torch.zeros((nz, nb, dim), dtype=torch.float32, device=dev)
         # the upstream scalar gradients stay on the device (no float(): that would drain the stream)
