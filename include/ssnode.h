@@ -138,8 +138,10 @@ SSN_API int ssn_host_gather(const void *const *items, int n, size_t bytes, void 
  * Implicit-function-theorem generator gradient at the fixed points:
  *   (I - W^T Phi) mu = g,   dL/dW = (Phi mu) r^T,   dL/dtheta = <dL/dW, dW/dtheta>
  * with Phi = diag f'(W r + ext) (SS_grad.py:45-59) and g = dL/dr.  The adjoint
- * system is solved by the damped iteration mu <- mu + eps (g - mu + W^T Phi mu),
- * eps = dt/tau, which contracts wherever the forward Euler scheme does.
+ * system is solved by restarted GMRES(16), the eight stimuli of a panel in lockstep,
+ * restarted from the true residual (environment SSN_IFT=damped selects the damped
+ * iteration mu <- mu + eps (g - mu + W^T Phi mu), eps = dt/tau, of the first version;
+ * its stopping rule is max|d mu| < rtol max|g|).
  *
  *   z        float32 [nz][2N][2N]  (W is rebuilt on chip from z and jds)
  *   R, g     float32 [nz][nb][2N]  fixed points and dL/dr
@@ -147,8 +149,10 @@ SSN_API int ssn_host_gather(const void *const *items, int n, size_t bytes, void 
  *            (device pointer when mem = SSN_MEM_DEVICE; accumulated with atomics,
  *            zeroed by this call)
  *   mu       float32 [nz][nb][2N] out, may be NULL
- *   status   int32 [nz][nb] out (0 converged / 1 max_iter), iters likewise; may be NULL
- *   rtol     stop when max|d mu| < rtol * max|g| per (network, stimulus)
+ *   status   int32 [nz][nb] out: 0 converged; 1 tolerance not reached (max_iter sweeps, or the true residual
+ *            stopped shrinking: FP32 floor of an ill-conditioned system -- mu is still the best iterate);
+ *            iters = contractions with W^T spent on the solve; both may be NULL
+ *   rtol     stop when |g - (I - W^T Phi) mu|_2 <= rtol |g|_2 per (network, stimulus); <= 0 selects 1e-5
  *   grad_ext float32 [nz][nb][2N] out, may be NULL: dL/d ext = Phi mu (the gradient w.r.t. the stimulus
  *            input, needed by the heterogeneous-input generators, networks/ssn.py:645-727)
  */

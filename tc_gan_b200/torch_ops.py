@@ -85,7 +85,7 @@ def fixed_points(z, J, D, S, ext, solver=None, r_init=None, precise=False):
     return R, status, iters
 
 
-def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-6, return_mu=False, return_grad_ext=False):
+def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-5, return_mu=False, return_grad_ext=False):
     """dL/d(J, D, S) (three float64 [2, 2] CUDA tensors) from dL/dR at the fixed points R;
     with return_grad_ext also dL/d ext [nz, nb, 2N] (= Phi mu, for heterogeneous-input generators)."""
     _check_cuda(z, ext, R, grad_R)
@@ -114,7 +114,7 @@ def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-6, return_mu=F
 
 
 # (status, iters) of the adjoint solves of the most recent implicit-gradient backward, device tensors
-# [nz, nb]: status 1 = the damped adjoint iteration hit max_iter (marginally stable fixed point).  Reading
+# [nz, nb]: status 1 = the adjoint solve did not reach rtol (marginally stable fixed point).  Reading
 # them synchronises; `adjoint_failures()` does so on demand.
 last_adjoint = {'status': None, 'iters': None}
 
