@@ -30,6 +30,8 @@ struct IoConst {
     T tanh_scale;                  // n r_soft / (span v0)
     T gain_hi;                     // n r_soft / v0
     T nk;                          // n k
+    int n_int;                     // floor(n), capped at 8: v^n = v^n_int * v^n_frac (io_power_fast)
+    T n_frac;
 };
 
 template <typename T>
@@ -43,6 +45,8 @@ inline IoConst<T> make_io_const(int io_type, double k, double n, double r_soft, 
     c.tanh_scale = (T)(n * r_soft / ((r_hard - r_soft) * v0));
     c.gain_hi = (T)(n * r_soft / v0);
     c.nk = (T)(n * k);
+    c.n_int = n >= 1.0 ? (n < 8.0 ? (int)n : 8) : 0;
+    c.n_frac = (T)(n - c.n_int);
     return c;
 }
 

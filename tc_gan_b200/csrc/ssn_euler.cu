@@ -13,9 +13,15 @@
 //
 // Forward and the adjoint recursion run on the cluster-resident machinery of K1/K2
 // (W, then W^T, in distributed shared memory; one DSMEM exchange per time step).
+//
+// Exchange: no cluster barrier inside the time loop.  A thread publishes its outputs of step t with st.async into
+// panel buffer (t+1)&1 of every CTA of the cluster (its own included); the stores complete bytes on that buffer's
+// mbarrier in the destination CTA, and a CTA starts step t+1 when 2N x 8 x 4 bytes have landed.  Double buffering
+// is enough: a peer can publish step t+1 only after its step-t+1 contraction, which needs every output of step t
+// of this CTA, i.e. all of this CTA's warps are past their reads of the buffer being overwritten.
 #include <cstdlib>
 #include <cstring>
-#include "ssn_cluster_core.cuh"
+#include "ssn_ws_common.cuh"
 #include "ssn_launch.h"
 
 namespace ssn {
@@ -53,6 +59,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
     constexpr int TO = Own::TO;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double red[2];
+    __shared__ __align__(8) unsigned long long bars[2];      // "panel buffer b is complete", one phase per use
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int csize = a.shape.csize;
@@ -82,20 +89,45 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
     for (int u = 0; u < TO; ++u)
         valid[u] = (Own::first_row(kl) + u < TI) && (own0 + u < rows_here);
 
-    unsigned xpeer[MAX_CLUSTER];
+    unsigned xpeer[MAX_CLUSTER], bpeer[MAX_CLUSTER];
 #pragma unroll
-    for (int p = 0; p < MAX_CLUSTER; ++p) xpeer[p] = map_to_rank(smem_u32(Xf), p < csize ? p : 0);
+    for (int p = 0; p < MAX_CLUSTER; ++p) {
+        xpeer[p] = map_to_rank(smem_u32(Xf), p < csize ? p : 0);
+        bpeer[p] = map_to_rank(smem_u32(&bars[0]), p < csize ? p : 0);
+    }
 
     build_profile_table(a.wc, N, gtab, tid, nthreads);
     for (int i = tid; i < 2 * 2 * P * 4; i += nthreads) Xf[i] = 0.f;
     if (tid < 2) red[tid] = 0.0;
+    if (tid == 0) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     const int n_chunks = (a.nb + TB - 1) / TB;
     const unsigned buf_bytes = 2u * (unsigned)P * 16u;
+    const unsigned step_bytes = (unsigned)dim * TB * 4u;       // every (row, stimulus slot) of the panel, once per step
     const int seqlen = a.seqlen, skip = a.skip;
     const int T = seqlen - skip;
     double pen_dyn = 0.0, pen_rate = 0.0;
+    unsigned phase = 0u;                                        // bit b: parity of the next completion of bars[b]
+    // publish one value per owned row into buffer nb of every CTA, then wait for the whole panel of that buffer
+    auto exchange = [&](const float (&val)[TO], const unsigned (&xo)[TO], int nb) {
+        const unsigned boff = nb ? buf_bytes : 0u;
+#pragma unroll
+        for (int u = 0; u < TO; ++u)
+            if (valid[u]) {
+#pragma unroll
+                for (int p = 0; p < MAX_CLUSTER; ++p)
+                    if (p < csize) st_async_u32(xpeer[p] + xo[u] + boff, __float_as_uint(val[u]), bpeer[p] + 8u * nb);
+            }
+        const unsigned bar = smem_u32(&bars[nb]);
+        if (tid == 0) mbar_arrive_expect_tx(bar, step_bytes);
+        mbar_wait(bar, (phase >> nb) & 1u);
+        phase ^= 1u << nb;
+    };
 
     for (;;) {
         if (rank == 0 && tid == 0) {
@@ -149,39 +181,40 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                 }
                 cluster.sync();
                 int buf = 0;
+                float eps_f[TO];
+#pragma unroll
+                for (int u = 0; u < TO; ++u) eps_f[u] = (float)eps_own[u];
+                const bool pure_power = a.io.io_type == SSN_IO_POWER;
                 for (int t = 0; t < seqlen; ++t) {
-                    float acc[TI][TB], v[TO];
+                    float acc[TI][TB], v[TO], rpub[TO];
                     contract_panel<TI, KL>(acc, Wsm, X4, P, kpad, buf, wrow, kl);
                     reduce_scatter<TI, KL>(acc, v, kl);
                     const int nbuf = buf ^ 1;
+                    const bool keep = t >= skip;
 #pragma unroll
-                    for (int u = 0; u < TO; ++u)
-                        if (valid[u]) {
-                            const float vt = v[u] + ext_own[u];
-                            const float fv = io_eval<float>(a.io, vt);
-                            // f' from f on the power branch (f' = n f / v): one powf per output instead of two
-                            const bool pw = vt > 0.f && (a.io.io_type == SSN_IO_POWER || vt <= a.io.v0);
-                            const double r_old = state[u];
-                            const double r_new = r_old + ((double)fv - r_old) * eps_own[u];
-                            state[u] = r_new;
-                            if (active) {
-                                if (t >= skip) {
-                                    avg[u] += r_new;
-                                    pen_rate += fmax(r_new - (double)a.threshold, 0.0);
-                                    if (t > skip) pen_dyn += (r_new - r_old) * (r_new - r_old);
-                                }
-                                const size_t o = net_base + (size_t)t * tslice + toff[u];
-                                if (a.traj) a.traj[o] = (float)r_new;
-                                if (a.gain)
-                                    a.gain[o] = (float)eps_own[u] * (pw ? a.io.n * fv / vt : io_gain<float>(a.io, vt));
-                            }
-                            const unsigned off = xoff[u] + (nbuf ? buf_bytes : 0u);
-                            const float rf = (float)r_new;
-#pragma unroll
-                            for (int p = 0; p < MAX_CLUSTER; ++p)
-                                if (p < csize) st_cluster_f32(xpeer[p] + off, rf);
+                    for (int u = 0; u < TO; ++u) {
+                        const float vt = v[u] + ext_own[u];
+                        float fv = 0.f, gv = 0.f;
+                        if (vt > 0.f) {
+                            if (pure_power || vt <= a.io.v0) io_power_fast(a.io, vt, fv, gv);
+                            else { fv = io_eval<float>(a.io, vt); gv = io_gain<float>(a.io, vt); }    // saturating branch
                         }
-                    cluster.sync();
+                        const double r_old = state[u];
+                        const double r_new = r_old + ((double)fv - r_old) * eps_own[u];
+                        state[u] = r_new;
+                        rpub[u] = (float)r_new;
+                        if (valid[u] && active) {
+                            if (keep) {
+                                avg[u] += r_new;
+                                pen_rate += fmax(r_new - (double)a.threshold, 0.0);
+                                if (t > skip) pen_dyn += (r_new - r_old) * (r_new - r_old);
+                            }
+                            const size_t o = net_base + (size_t)t * tslice + toff[u];
+                            if (a.traj) a.traj[o] = rpub[u];
+                            if (a.gain) a.gain[o] = eps_f[u] * gv;
+                        }
+                    }
+                    exchange(rpub, xoff, nbuf);
                     buf = nbuf;
                 }
 #pragma unroll
@@ -204,7 +237,15 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                 int buf = 0;
                 for (int tp = seqlen - 1; tp >= 0; --tp) {
                     const int k = tp + 1;
-                    float y[TO];
+                    // operands of this step from HBM, requested before the contraction that hides their latency
+                    float gain_k[TO], r_prevs[TO];
+#pragma unroll
+                    for (int u = 0; u < TO; ++u) {
+                        const bool ld = valid[u] && active;
+                        gain_k[u] = ld ? __ldg(a.gain_in + net_base + (size_t)tp * tslice + toff[u]) : 0.f;
+                        r_prevs[u] = (ld && tp > 0) ? __ldg(a.traj_in + net_base + (size_t)(tp - 1) * tslice + toff[u]) : 0.f;
+                    }
+                    float y[TO], qpub[TO];
 #pragma unroll
                     for (int u = 0; u < TO; ++u) y[u] = 0.f;
                     if (k < seqlen) {                   // q_k was published at the end of the previous step
@@ -214,12 +255,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                     }
                     const int nbuf = buf ^ 1;
 #pragma unroll
-                    for (int u = 0; u < TO; ++u)
+                    for (int u = 0; u < TO; ++u) {
+                        qpub[u] = 0.f;
                         if (valid[u]) {
-                            float r_prev = 0.f;
+                            const float r_prev = r_prevs[u];
                             double lam = 0.0;
                             if (active) {
-                                if (tp > 0) r_prev = __ldg(a.traj_in + net_base + (size_t)(tp - 1) * tslice + toff[u]);
                                 double d = 0.0;
                                 if (k >= skip + 1) {
                                     d = (double)gavg[u];
@@ -233,7 +274,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                             // q_{k-1} = gain[k-1] * lambda_k, paired with r_{k-1} = traj[tp-1]
                             float q = 0.f;
                             if (active) {
-                                q = __ldg(a.gain_in + net_base + (size_t)tp * tslice + toff[u]) * (float)lam;
+                                q = gain_k[u] * (float)lam;
                                 gext[u] += q;                             // dL/d ext = sum_k q_k, q_0 included
                                 if (tp > 0) a.adj[net_base + (size_t)(tp - 1) * tslice + toff[u]] = q;
                                 else q = 0.f;                             // q_0 pairs with r_0 = 0: nothing to publish
@@ -242,12 +283,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                                 a.adj[net_base + (size_t)tp * tslice + toff[u]] = 0.f;   // q_seqlen = 0
                             r_next[u] = r_cur[u];
                             r_cur[u] = r_prev;
-                            const unsigned off = xoff[u] + (nbuf ? buf_bytes : 0u);
-#pragma unroll
-                            for (int p = 0; p < MAX_CLUSTER; ++p)
-                                if (p < csize) st_cluster_f32(xpeer[p] + off, q);
+                            qpub[u] = q;
                         }
-                    cluster.sync();
+                    }
+                    exchange(qpub, xoff, nbuf);
                     buf = nbuf;
                 }
                 if (a.grad_ext) {
