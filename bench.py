@@ -268,6 +268,7 @@ def time_gan_step(workload, steps, warmup, dev, world, rank, peak):
     torch.cuda.synchronize()
     kernels = clib.profile_read()
     clib.profile_enable(False)
+    t_end = time.time()
     launches = clib.kernel_launches() - launches0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -346,6 +347,91 @@ def time_nb50_slice(dev, peak, nz=128):
     return {'workload': 'configs[4] shape: %d networks x 50 stimuli (5 contrasts x 10 bandwidths), 2N=402, device-side z' % nz,
             'value': conv / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'converged': conv, 'solves': nz * nb,
             'mean_sweeps_per_solve': sweeps / (nz * nb), 'fp32_roofline_frac': tf / peak}
+
+
+def run_sweep(args):
+    """`--workload sweep`: configs[4] at full size -- 65536 networks x 50 stimuli at 2N=402, z drawn on the device
+    (torch Philox, a fresh slab per launch), the networks split evenly over the ranks (strong scaling, no collective
+    on the data path; the converged counts and the max time are reduced once after the timed region)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tc_gan_b200 import clib, ssnode, stimuli
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    total, slab = args.sweep_networks, 512
+    mine = total // world + (1 if rank < total % world else 0)
+    P = ssnode.DEFAULT_PARAMS
+    jds = ssnode.new_JDS()
+    exts_np = stimuli.input(np.linspace(0, 1, 10), np.linspace(-.5, .5, N_SITES), P['smoothness'], [5, 10, 20, 30, 40])
+    nb = len(exts_np)
+    ext = torch.tensor(exts_np, dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(777 + rank)
+    z = [torch.empty((slab, DIM, DIM), device=dev) for _ in range(2)]
+    R = torch.empty((slab, nb, DIM), dtype=torch.float32, device=dev)
+    status = torch.empty((slab, nb), dtype=torch.int32, device=dev)
+    iters = torch.empty((slab, nb), dtype=torch.int32, device=dev)
+    conv = torch.zeros((), dtype=torch.int64, device=dev)
+    sweeps = torch.zeros((), dtype=torch.int64, device=dev)
+    sv = clib.make_solver(k=P['k'], n=P['n'])
+    jd = clib.make_jds(jds['J'], jds['D'], jds['S'])
+    stream = torch.cuda.current_stream()
+
+    def solve(zz, n):
+        clib.check_call(clib.libssnode.ssn_fixed_point_batch(
+            sv, n, nb, N_SITES, clib.W_FROM_Z, zz.data_ptr(), jd, ext.data_ptr(), 0, None, R.data_ptr(),
+            status.data_ptr(), iters.data_ptr(), 0, clib.MEM_DEVICE, stream.cuda_stream), 'ssn_fixed_point_batch')
+
+    z[0].uniform_(generator=gen)
+    solve(z[0], min(slab, 64))                                  # warm-up (module load, occupancy queries)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local_rank)
+    t_start = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = clib.kernel_launches()
+    e0.record()
+    done, i = 0, 0
+    while done < mine:
+        n = min(slab, mine - done)
+        z[i & 1].uniform_(generator=gen)                        # Philox z on the device, inside the timed region
+        solve(z[i & 1], n)
+        conv += (status[:n] == 0).sum()
+        sweeps += iters[:n].sum(dtype=torch.int64)
+        done += n
+        i += 1
+    e1.record()
+    torch.cuda.synchronize()
+    t_end = time.time()
+    launches = clib.kernel_launches() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tot = torch.stack([conv, sweeps]).to(torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    clk = clocks.stop(t_start, t_end)
+    if rank == 0:
+        sec = ms.item() * 1e-3
+        peak = fp32_peak_tflops(clk.get('sm_max_mhz')) * world
+        tf = tot[1].item() * FLOP_PER_SWEEP / sec * 1e-12
+        print(json.dumps({
+            'metric': 'converged SSN solves/sec (2N=402, 50 stim)', 'value': tot[0].item() / sec, 'unit': UNIT,
+            'n_gpus': world, 'steps': 1, 'warmup': 1, 'ms_per_step': ms.item(), 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32 contraction / f64 state', 'data': 'synthetic',
+            'config': {'workload': 'configs[4]: throughput sweep, %d networks x %d stimuli (5 contrasts x 10 bandwidths), '
+                                   '2N=402, device-side Philox z, slabs of %d networks' % (total, nb, slab),
+                       'networks_per_gpu': mine, 'l2': 'a fresh z slab (331 MB) per launch'},
+            'converged': int(tot[0].item()), 'solves': total * nb, 'mean_sweeps_per_solve': tot[1].item() / (total * nb),
+            'gpu_launches': launches, 'clocks': clk,
+            'roofline': {'bound': 'fp32_ffma', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak}}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_secondary_only(args):
@@ -436,13 +522,17 @@ def main():
     ap.add_argument('--networks', type=int, default=NZ, help='networks per GPU per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the GAN-step / 50-stimulus secondary block')
-    ap.add_argument('--workload', default='solve', choices=['solve', 'gan_fp', 'gan_bptt', 'wgan_fp', 'wgan_bptt'],
+    ap.add_argument('--workload', default='solve', choices=['solve', 'gan_fp', 'gan_bptt', 'wgan_fp', 'wgan_bptt', 'sweep'],
                     help='solve: configs[1] (default, the BASELINE metric, with the secondary block); gan_fp / gan_bptt: '
-                         'only that generator step; wgan_*: full WGAN-GP training steps')
+                         'only that generator step; wgan_*: full WGAN-GP training steps; sweep: configs[4], the '
+                         '65536-network x 50-stimulus throughput sweep split over the ranks')
+    ap.add_argument('--sweep-networks', type=int, default=65536, help='total networks of --workload sweep')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload == 'sweep':
+        return run_sweep(args)
     if args.workload in ('wgan_fp', 'wgan_bptt'):
         return run_wgan(args)
     if args.workload != 'solve':
