@@ -149,10 +149,11 @@ SSN_API int ssn_host_gather(const void *const *items, int n, size_t bytes, void 
  *            (device pointer when mem = SSN_MEM_DEVICE; accumulated with atomics,
  *            zeroed by this call)
  *   mu       float32 [nz][nb][2N] out, may be NULL
- *   status   int32 [nz][nb] out: 0 converged; 1 tolerance not reached (max_iter sweeps, or the true residual
- *            stopped shrinking: FP32 floor of an ill-conditioned system -- mu is still the best iterate);
+ *   status   int32 [nz][nb] out: 0 converged (or stalled at the FP32 floor of the residual within 16 rtol);
+ *            1 tolerance not reached (max_iter sweeps, or the true residual stopped shrinking above 16 rtol:
+ *            ill-conditioned system -- mu is still the best iterate);
  *            iters = contractions with W^T spent on the solve; both may be NULL
- *   rtol     stop when |g - (I - W^T Phi) mu|_2 <= rtol |g|_2 per (network, stimulus); <= 0 selects 1e-5
+ *   rtol     stop when |g - (I - W^T Phi) mu|_2 <= rtol |g|_2 per (network, stimulus); <= 0 selects 1e-6
  *   grad_ext float32 [nz][nb][2N] out, may be NULL: dL/d ext = Phi mu (the gradient w.r.t. the stimulus
  *            input, needed by the heterogeneous-input generators, networks/ssn.py:645-727)
  */

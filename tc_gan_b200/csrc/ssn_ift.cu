@@ -439,7 +439,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                         if (bnew <= tolabs) { sdone = true; my_status = 0; }
                         else {
                             stagnant = bnew < 0.9f * beta ? 0 : stagnant + 1;         // false for NaN too
-                            if (stagnant >= 2 || sweeps >= a.max_iter || !(bnew == bnew)) sdone = true;
+                            if (stagnant >= 2 || sweeps >= a.max_iter || !(bnew == bnew)) {
+                                // the true residual (FP32 contraction) no longer shrinks: this is the floor of the
+                                // arithmetic, ~1e-7 |W^T Phi mu|; accepted as converged within 16 x the tolerance
+                                sdone = true;
+                                if (bnew <= 16.f * tolabs) my_status = 0;
+                            }
                         }
                         beta = bnew;
                         if (sdone && cta_writer) atomicOr(&ctl[0], 1u << my_stim);
@@ -669,7 +674,7 @@ int launch_ift_gradient(const ssn_solver &sv, int nz, int nb, int n_sites, const
     a.R = R; a.g = g; a.mu = mu; a.grad_ext = grad_ext; a.status = status; a.iters = iters; a.grad = grad; a.work_counter = counter;
     a.io = make_io_const<float>(sv.io_type, sv.k, sv.n, sv.rate_soft_bound, sv.rate_hard_bound);
     a.eps_E = sv.dt / sv.tau_E; a.eps_I = sv.dt / sv.tau_I;
-    a.rtol = rtol > 0 ? rtol : 1e-5;
+    a.rtol = rtol > 0 ? rtol : 1e-6;
     a.max_iter = sv.max_iter;
 
     cudaLaunchConfig_t cfg = {};

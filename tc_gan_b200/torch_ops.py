@@ -85,7 +85,7 @@ def fixed_points(z, J, D, S, ext, solver=None, r_init=None, precise=False):
     return R, status, iters
 
 
-def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-5, return_mu=False, return_grad_ext=False):
+def ift_gradient(z, J, D, S, ext, R, grad_R, solver=None, rtol=1e-6, return_mu=False, return_grad_ext=False):
     """dL/d(J, D, S) (three float64 [2, 2] CUDA tensors) from dL/dR at the fixed points R;
     with return_grad_ext also dL/d ext [nz, nb, 2N] (= Phi mu, for heterogeneous-input generators)."""
     _check_cuda(z, ext, R, grad_R)
