@@ -210,6 +210,13 @@ def dist_env():
             int(os.environ.get('WORLD_SIZE', '1')))
 
 
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        return {}
+
+
 def fp32_peak_tflops(sm_max_mhz):
     return 148 * 128 * 2 * (sm_max_mhz or 1965.0) * 1e6 * 1e-12
 
@@ -290,11 +297,20 @@ def time_gan_step(workload, steps, warmup, dev, world, rank, peak):
         flop['ssn_euler_cluster_kernel_fwd'] = nz * 8 * seqlen * FLOP_PER_SWEEP
         flop['ssn_euler_cluster_kernel_bwd'] = nz * 8 * (seqlen - 1) * FLOP_PER_SWEEP
         flop['ssn_bptt_param_grad_kernel'] = nz * 8 * seqlen * FLOP_PER_SWEEP
+        flop['ssn_bptt_param_grad_tc_kernel'] = nz * 8 * seqlen * FLOP_PER_SWEEP
     for name, (tot_ms, n) in sorted(kernels.items()):
         ent = {'ms_per_launch': tot_ms / n, 'launches_per_step': n / steps}
         if flop.get(name):
             ent['tflops'] = flop[name] / (tot_ms / n * 1e-3) * 1e-12
             ent['fp32_roofline_frac'] = ent['tflops'] / peak
+        if name == 'ssn_bptt_param_grad_tc_kernel' and flop.get(name):
+            # tensor-pipe view: three kind::tf32 MMAs per product (hi/lo split) on 128 x 208 tiles of the 402 x 402
+            # output (512 x 416 computed); peak = half the measured dense bf16 rate (TF32 runs at half the bf16 rate;
+            # nominal 1.1 PFLOP/s, /opt/skills/guides/B200_PROFILING.md)
+            executed = ent['tflops'] * 3.0 * (512.0 * 416.0) / float(DIM * DIM)
+            tpeak = measured_peaks().get('bf16_tflops_sustained', 2250.0) / 2.0
+            ent['tensor'] = {'executed_tflops': executed, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': executed / tpeak,
+                             'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained / 2'}
         per_kernel[name] = ent
     return {'metric': 'GAN generator steps/sec (%s)' % ('fixed-point, implicit gradient' if workload == 'gan_fp'
                                                         else 'BPTT, seqlen 1200'),

@@ -20,3 +20,12 @@ for rep in range(int(os.environ.get('REPS', 2))):
     ((avg * G).sum() + 0.1 * dyn + 0.01 * rate).backward()
 torch.cuda.synchronize()
 print('ok', int((st == 0).sum()), float(J.grad.abs().sum()))
+if os.environ.get('F64'):
+    # the reference-ABI symbol (float64 cluster kernel): one (network, stimulus) per call, and one batched precise call
+    from tc_gan_b200 import weight_gen
+    zz = z[0].double().cpu().numpy()
+    W = weight_gen.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], zz)
+    e64 = exts.double().cpu().numpy()
+    sol = ssnode.fixed_point(W, e64[7], k=P['k'], n=P['n'])
+    Rs, errs, its = ssnode.fixed_points_batch(np.stack([W] * 8), e64, precise=True, k=P['k'], n=P['n'])
+    print('f64 ok', sol.error, int((errs == 0).sum()))
