@@ -53,6 +53,45 @@ def test_ift_gradient_matches_oracle(ops, oracle, n_sites, nz, nb, io_type):
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
 
 
+@pytest.mark.parametrize('n_sites,nz,nb', [(1, 3, 2), (3, 2, 9), (17, 4, 8), (64, 2, 16), (201, 3, 8)])
+def test_ift_gmres_residual_and_damped_agreement(ops, oracle, monkeypatch, n_sites, nz, nb):
+    """The restarted GMRES of K2 (default) against (a) the defining linear system, checked in float64 on the host:
+    |g - (I - W^T Phi) mu|_2 <= ~rtol |g|_2 per solve, and (b) the damped adjoint iteration of round 1
+    (SSN_IFT=damped), which it replaces: same gradients to 2e-4, in at least 4x fewer contractions at 2N >= 34.
+    Sizes include 2N = 2 (Krylov space exhausted after two steps: the breakdown branch), a ragged stimulus count
+    with a partly empty second panel, and BASELINE's 2N = 402."""
+    import torch
+    jds = oracle.new_JDS()
+    dim = 2 * n_sites
+    exts = oracle.stimulus_input(np.linspace(0.05, 1, nb), n_sites) if n_sites > 1 else np.full((nb, 2), 5.0) * (1 + np.arange(nb))[:, None]
+    rs = np.random.RandomState(100 + n_sites)
+    z = rs.rand(nz, dim, dim).astype(np.float32).astype(np.float64)
+    W = oracle.generate_weight(n_sites, jds['J'], jds['D'], jds['S'], z)
+    R, st, _ = oracle.fixed_point_batch(W, exts, threads=8)
+    assert (st == 0).all()
+    R = R.astype(np.float32).astype(np.float64)
+    gR = rs.randn(nz, nb, dim).astype(np.float32).astype(np.float64)
+    J, D, S = (tens(jds[k], torch.float64) for k in 'JDS')
+    args = (tens(z), J, D, S, tens(exts), tens(R), tens(gR))
+    gm = ops.ift_gradient(*args, rtol=1e-6, return_mu=True)
+    mu, status, iters = (t.cpu().numpy() for t in gm[3:6])
+    assert (status == 0).all()
+    for iz in range(nz):
+        for ib in range(nb):
+            phi = oracle.io_gain(W[iz] @ R[iz, ib] + exts[ib])
+            res = gR[iz, ib] - mu[iz, ib] + W[iz].T @ (phi * mu[iz, ib])
+            # 1e-6 asked; float32 storage of mu adds ~6e-8 |A mu|
+            assert np.linalg.norm(res) <= 4e-6 * np.linalg.norm(gR[iz, ib]) + 2e-7 * np.linalg.norm(mu[iz, ib])
+    monkeypatch.setenv('SSN_IFT', 'damped')
+    dm = ops.ift_gradient(*args, rtol=1e-6, return_mu=True)
+    monkeypatch.delenv('SSN_IFT')
+    assert (dm[4].cpu().numpy() == 0).all()
+    for a, b in zip(gm[:3], dm[:3]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-4, atol=2e-4 * float(b.abs().max()))
+    if n_sites >= 17:
+        assert iters.mean() * 4 < dm[5].cpu().numpy().mean()
+
+
 def test_fixed_point_autograd_function(ops, oracle):
     """loss = <R, G> through SSNFixedPoint.apply; J.grad etc. against the oracle, and the
     zero-gradient / ragged-panel edge cases."""
