@@ -8,12 +8,13 @@
 // with Phi = diag f'(W r + I) and g = dL/dr.  The adjoint system is solved by restarted GMRES(16) on the
 // cluster-resident machinery of K1 (here the cluster holds W^T in shared memory): one Arnoldi step is one
 // skinny contraction W^T (Phi v) of the 8-stimulus panel -- the eight systems of a network share W^T, differ in
-// Phi and run in lockstep -- plus one cluster-wide reduction of the classical Gram-Schmidt coefficients.  The
-// Krylov basis lives in an L2-resident scratch (17 vectors x 13 KB per network), the small least-squares problem
+// Phi and run in lockstep -- plus two cluster-wide reductions (Gram-Schmidt coefficients; norm of the new vector).  The
+// Krylov basis lives in an L2-resident scratch (16 vectors x 16 KB per resident cluster), the small least-squares problem
 // is updated with Givens rotations per stimulus, and every cycle starts from the TRUE residual g - A mu, which
 // is also the stopping test: ||g - A mu||_2 <= rtol ||g||_2.  Against the damped adjoint iteration
 // mu <- mu + eps (g - mu + W^T Phi mu) of round 1 (still here: SSN_IFT=damped) this needs ~45 instead of ~500
-// sweeps per panel at 2N = 402 and ends 20x closer to the exact solution (2e-6 instead of 4e-5).
+// sweeps per panel at 2N = 402 (27 instead of 417 per solve) and ends 20x closer to the exact solution (2e-6
+// instead of 4e-5).
 //
 // Per network and 8-stimulus panel:  (1) W in smem, one contraction v = W r + I -> Phi;  (2) W^T in smem,
 // GMRES;  (3) fused reduction of (Phi mu)_i r_j against dW_ij/dtheta (z re-read from global, never
@@ -51,7 +52,7 @@ constexpr int RPK = GM * (GM + 1) / 2;                 // packed upper-triangula
 constexpr int IFT_NWARPS = 8;
 // shared-memory scratch of the GMRES path, in floats: per-warp partial sums, per-CTA partial sums of every peer, the
 // reduced values, R and the rotated right-hand side per stimulus, two control words
-constexpr int IFT_EXTRA_FLOATS = IFT_NWARPS * TB * GNV + MAX_CLUSTER * TB * GNV + TB * GNV + TB * RPK + TB * (GM + 1) + 4;
+constexpr int IFT_EXTRA_FLOATS = IFT_NWARPS * TB * GNV + MAX_CLUSTER * TB * GNV + TB * GNV + TB * RPK + TB * (GM + 1) + 4 + TB * GNV;
 constexpr int IFT_EXTRA_SMEM = ((IFT_EXTRA_FLOATS * 4 + 15) / 16) * 16;
 
 // sum over the lanes of a warp that own the same stimulus (lane l owns stimulus (l % KL) / (KL / 8))
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                 float *Rp = fin + TB * GNV;                                       // [TB][RPK]
                 float *gam = Rp + TB * RPK;                                       // [TB][GM + 1]
                 unsigned *ctl = reinterpret_cast<unsigned *>(gam + TB * (GM + 1)); // [0] finished solves, [1] frozen in this cycle
+                float *fin2 = reinterpret_cast<float *>(ctl + 4);                 // [TB][GNV], second reduction of a step
                 const bool warp_writer = (lane / KL == 0) && (kl % Own::SPLIT == 0);
                 const bool cta_writer = warp == 0 && warp_writer;
                 float4 *bas = a.basis + (size_t)(blockIdx.x / csize) * GM * TO4 * csize * nthreads + rank * nthreads + tid;
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                 const float *fin_mine = fin + my_stim * GNV;
 
                 // sum of the nv values per stimulus every warp has left in wpart -> fin (identical in every CTA)
-                auto cluster_sum = [&](int nv) {
+                auto cluster_sum = [&](int nv, float *dst) {
                     __syncthreads();
                     const int b = tid / nv, i = tid - b * nv;
                     if (tid < TB * nv) {
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                     if (tid < TB * nv) {
                         float sacc = 0.f;
                         for (int p = 0; p < csize; ++p) sacc += cpart[(p * TB + b) * GNV + i];
-                        fin[b * GNV + i] = sacc;
+                        dst[b * GNV + i] = sacc;
                     }
                     __syncthreads();
                 };
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                     p = stim_lane_sum<KL>(p);
                     if (warp_writer) wp_mine[0] = p;
                 }
-                cluster_sum(1);
+                cluster_sum(1, fin);
                 // A solve whose dL/dr vanishes (e.g. a rejected network masked out by the caller) has mu = 0: it is
                 // finished before the first sweep and contributes nothing, whatever (possibly non-finite) state R holds.
                 for (int b = 0; b < TB; ++b)
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                             for (int u = 0; u < TO; ++u) wv[u] = valid[u] ? vcur[u] - y[u] : 0.f;   // w = A v_j
                         }
                         ++sweeps;
-                        // classical Gram-Schmidt: h_i = <w, v_i> (i <= j) and |w|^2 in ONE cluster reduction
+                        // classical Gram-Schmidt: h_i = <w, v_i> (i <= j), one cluster reduction ...
                         for (int i = 0; i <= j; ++i) {
                             float vi[TO], p = 0.f;
                             load_vec(i, vi);
@@ -313,30 +315,41 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                             p = stim_lane_sum<KL>(p);
                             if (warp_writer) wp_mine[i] = p;
                         }
+                        cluster_sum(j + 1, fin);
+                        // ... w' = w - sum h_i v_i, and a second (one value) reduction for |w'|^2.  Taking the norm from
+                        // |w|^2 - sum h_i^2 instead would save this barrier, but it is unstable here: the systems are
+                        // I - (small), so h_jj ~ 1 >> |w'|, a 0.1 % error in the norm of v_j becomes a 50 % error in
+                        // |w'|^2 one step later and the basis blows up within a cycle (measured: estimated residuals off
+                        // by 1e30, cycles that increase the true residual; with the true norm the ratio stays below 7
+                        // and the solves need ~12 % fewer contractions).
+                        float vnext[TO], hsq = 0.f;
+#pragma unroll
+                        for (int u = 0; u < TO; ++u) vnext[u] = wv[u];
+                        if (!frozen)
+                            for (int i = 0; i <= j; ++i) {
+                                float vi[TO];
+                                load_vec(i, vi);
+                                const float h = fin_mine[i];
+                                hsq = fmaf(h, h, hsq);
+#pragma unroll
+                                for (int u = 0; u < TO; ++u) vnext[u] = fmaf(-h, vi[u], vnext[u]);
+                            }
                         {
                             float p = 0.f;
 #pragma unroll
-                            for (int u = 0; u < TO; ++u) p = fmaf(wv[u], wv[u], p);
+                            for (int u = 0; u < TO; ++u) p = fmaf(vnext[u], vnext[u], p);
                             p = stim_lane_sum<KL>(p);
-                            if (warp_writer) wp_mine[j + 1] = p;
+                            if (warp_writer) wp_mine[0] = p;
                         }
-                        cluster_sum(j + 2);
-                        float vnext[TO];
-#pragma unroll
-                        for (int u = 0; u < TO; ++u) vnext[u] = 0.f;
+                        cluster_sum(1, fin2);
                         if (!frozen) {
                             // new column of the Hessenberg matrix, rotated into R (every thread of the stimulus
                             // computes the same numbers; one of them records R and the rotated right-hand side)
                             float col[GM + 1];
-                            const float ww = fin_mine[j + 1];
-                            float hsq = 0.f;
 #pragma unroll
-                            for (int i = 0; i < GM; ++i) {
-                                col[i] = i <= j ? fin_mine[i] : 0.f;
-                                hsq = fmaf(col[i], col[i], hsq);
-                            }
-                            const float hn2 = ww - hsq;                       // |w - sum h_i v_i|^2 (Pythagoras)
-                            const bool brk = !(hn2 > 1e-5f * ww);             // (nearly) invariant subspace, or NaN
+                            for (int i = 0; i < GM; ++i) col[i] = i <= j ? fin_mine[i] : 0.f;
+                            const float hn2 = fin2[my_stim * GNV];                            // |w - sum h_i v_i|^2
+                            const bool brk = !(hn2 > 1e-9f * (hsq + hn2));    // Krylov space exhausted (or NaN)
                             const float hn = sqrtf(fmaxf(hn2, 0.f));
                             float gnext = 0.f;
 #pragma unroll
@@ -366,20 +379,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                             if (brk || fabsf(gnext) <= 0.7f * tolabs || j == GM - 1) {
                                 frozen = true;
                                 if (cta_writer) atomicOr(&ctl[1], 1u << my_stim);
+#pragma unroll
+                                for (int u = 0; u < TO; ++u) vnext[u] = 0.f;
                             } else {
                                 const float inv = 1.f / hn;
 #pragma unroll
-                                for (int u = 0; u < TO; ++u) vnext[u] = wv[u];
-                                for (int i = 0; i <= j; ++i) {
-                                    float vi[TO];
-                                    load_vec(i, vi);
-                                    const float h = fin_mine[i];
-#pragma unroll
-                                    for (int u = 0; u < TO; ++u) vnext[u] = fmaf(-h, vi[u], vnext[u]);
-                                }
-#pragma unroll
                                 for (int u = 0; u < TO; ++u) vnext[u] *= inv;
                             }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < TO; ++u) vnext[u] = 0.f;
                         }
 #pragma unroll
                         for (int u = 0; u < TO; ++u) vcur[u] = vnext[u];
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                         if (warp_writer) wp_mine[0] = p;
                     }
                     ++sweeps;
-                    cluster_sum(1);
+                    cluster_sum(1, fin);
                     if (!sdone) {
                         const float bnew = sqrtf(fmaxf(fin_mine[0], 0.f));
                         my_iters = sweeps;
