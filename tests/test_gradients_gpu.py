@@ -90,6 +90,13 @@ def test_ift_gmres_residual_and_damped_agreement(ops, oracle, monkeypatch, n_sit
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-4, atol=2e-4 * float(b.abs().max()))
     if n_sites >= 17:
         assert iters.mean() * 4 < dm[5].cpu().numpy().mean()
+    # the fallback of a stalled GMRES (forced here after the first cycle): damped steps from the GMRES iterate
+    monkeypatch.setenv('SSN_IFT', 'stall')
+    fb = ops.ift_gradient(*args, rtol=1e-6, return_mu=True)
+    monkeypatch.delenv('SSN_IFT')
+    assert (fb[4].cpu().numpy() == 0).all()
+    for a, b in zip(fb[:3], gm[:3]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-4, atol=2e-4 * float(b.abs().max()))
 
 
 def test_fixed_point_autograd_function(ops, oracle):
