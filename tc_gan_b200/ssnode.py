@@ -325,6 +325,48 @@ def _stack(arrays, host_threads=0):
     return out
 
 
+class _Gather(object):
+    """Copy of the Z of one round of draws into rows [row0, row0 + n) of the output array, on a host thread that runs
+    beside the GPU call (both release the GIL)."""
+
+    def __init__(self, zs, out, row0, host_threads):
+        import threading
+        self.out = out
+        ptrs = (ctypes.c_void_p * len(zs))(*[z.ctypes.data for z in zs])
+        dst = out.ctypes.data + row0 * zs[0].nbytes
+        self._keep = (zs, ptrs)
+        self._rc = None
+
+        def run():
+            self._rc = libssnode.ssn_host_gather(ptrs, len(zs), zs[0].nbytes, dst, int(host_threads))
+        self._thread = threading.Thread(target=run)
+        self._thread.start()
+
+    def join(self):
+        self._thread.join()
+        clib.check_call(self._rc, 'ssn_host_gather')
+        return self.out
+
+
+def _start_gather(drawn, out, row0, num, host_threads):
+    """Start gathering the Z of `drawn` into the result array (allocated on the first round) when they are
+    equal-shaped contiguous ndarrays worth a threaded copy; None otherwise (the caller then stacks at the end)."""
+    zs = [Z for Z, _ in drawn]
+    first = zs[0]
+    if not (isinstance(first, np.ndarray) and first.nbytes >= 1 << 16 and all(
+            isinstance(z, np.ndarray) and z.shape == first.shape and z.dtype == first.dtype and
+            z.flags['C_CONTIGUOUS'] for z in zs)):
+        return None
+    if out is None:
+        if row0:
+            return None
+        out = np.empty((num,) + first.shape, dtype=first.dtype)
+    elif out.shape[1:] != first.shape or out.dtype != first.dtype:
+        return None
+    # a quarter of the threads: the solver's own staging threads need the memory bandwidth more
+    return _Gather(zs, out, row0, max(1, (host_threads or 16) // 4))
+
+
 def _generate_weight_from_z(Z, jds):
     from .weight_gen import generate_weight
     Z = np.asarray(Z, dtype='double')
@@ -373,11 +415,22 @@ def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
 
     kept_z, kept_R, kept_it = [], [], []
     counter = collections.Counter()
-    while len(kept_z) < num:
-        drawn = take(num - len(kept_z), Z_W_gen)
+    # The stacked `Zs` the reference returns (np.array(zs), ssnode.py:503-510) is a 1.3 GB copy at the benchmark
+    # size.  It is written WHILE the GPU solves the round: a host thread gathers the drawn Z into their final rows
+    # (most draws converge), and only the rows of rejected networks are closed up afterwards.
+    zs_out, zs_rows = None, 0
+    while zs_rows + len(kept_z) < num:
+        drawn = take(num - zs_rows - len(kept_z), Z_W_gen)
         if not drawn:
             break
-        Rs, errors, iters = _solve_drawn(drawn, exts, jds, precise, host_threads, **kwargs)
+        gather = _start_gather(drawn, zs_out, zs_rows, num, host_threads) if not kept_z else None
+        if gather is None and zs_out is not None:           # draws that no longer fit the array: back to a list
+            kept_z, zs_out, zs_rows = [z for z in zs_out[:zs_rows]], None, 0
+        try:
+            Rs, errors, iters = _solve_drawn(drawn, exts, jds, precise, host_threads, **kwargs)
+        finally:
+            if gather is not None:
+                zs_out = gather.join()
         ok = (errors == 0).all(axis=1) & np.isfinite(Rs).all(axis=(1, 2))
         for i in np.flatnonzero(~ok):
             err = errors[i].copy()
@@ -388,10 +441,24 @@ def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
             counter[sol.error] += 1
             if check:
                 raise sol.to_exception()
-        kept_z.extend(drawn[i][0] for i in np.flatnonzero(ok))
+        if gather is not None:
+            good = np.flatnonzero(ok)
+            if len(good) < len(drawn):                     # close up the rows of the rejected networks
+                for dst, src in enumerate(good):
+                    if dst != src:
+                        zs_out[zs_rows + dst] = zs_out[zs_rows + src]
+            zs_rows += len(good)
+        else:
+            kept_z.extend(drawn[i][0] for i in np.flatnonzero(ok))
         kept_R.append(Rs[ok])
         kept_it.append(iters[ok])
 
+    if zs_out is not None:
+        if zs_rows == 0:
+            raise ValueError('find_fixed_points: Z_W_gen was exhausted before any network converged')
+        xs, its = np.concatenate(kept_R), np.concatenate(kept_it)
+        Zs = zs_out if zs_rows == len(zs_out) else zs_out[:zs_rows].copy()
+        return Zs, xs, FixedPointsInfo(_Solutions(xs, its), counter, sum(counter.values()), 0)
     if not kept_z:
         raise ValueError('find_fixed_points: Z_W_gen was exhausted before any network converged')
     xs, its = np.concatenate(kept_R), np.concatenate(kept_it)
