@@ -27,7 +27,9 @@ def tens(a, dtype=None, grad=False):
 
 @pytest.mark.parametrize('n_sites,nz,nb,io_type', [(12, 2, 3, 'asym_tanh'), (51, 3, 8, 'asym_tanh'),
                                                    (51, 2, 8, 'asym_power'), (40, 2, 11, 'asym_linear'),
-                                                   (201, 2, 8, 'asym_tanh')])
+                                                   (201, 2, 8, 'asym_tanh'),
+                                                   # cluster widths 2 and 8 of the shared-memory core (4 is 2N = 402)
+                                                   (125, 2, 8, 'asym_tanh'), (280, 2, 5, 'asym_tanh')])
 def test_ift_gradient_matches_oracle(ops, oracle, n_sites, nz, nb, io_type):
     """Same R and dL/dR into the CUDA adjoint path and the float64 restatement of
     SS_grad.WRgrad_batch + make_w_batch + run/gan.py:902-911."""
@@ -137,7 +139,11 @@ def euler_oracle(oracle, z, jds, exts, seqlen, skip, eps, io_type, thr, G, c_dyn
 
 @pytest.mark.parametrize('n_sites,nz,nb,seqlen,skip,io_type', [
     (10, 2, 8, 60, 40, 'asym_tanh'), (25, 3, 5, 40, 25, 'asym_tanh'), (51, 2, 8, 30, 20, 'asym_power'),
-    (30, 2, 11, 24, 0, 'asym_linear'), (201, 1, 8, 12, 6, 'asym_tanh')])
+    (30, 2, 11, 24, 0, 'asym_linear'), (201, 1, 8, 12, 6, 'asym_tanh'),
+    # every cluster width of the shared-memory core: 1 CTA (2N = 2, 20), 2 (2N = 250), 4 (402 above), 8 (2N = 560);
+    # more networks than resident clusters of 8 (17 > 15), a ragged second panel
+    (1, 3, 2, 9, 3, 'asym_tanh'), (125, 3, 8, 16, 8, 'asym_tanh'), (280, 2, 8, 10, 4, 'asym_tanh'),
+    (280, 17, 3, 6, 2, 'asym_power'), (64, 40, 9, 14, 5, 'asym_tanh')])
 def test_euler_unroll_forward_backward(ops, oracle, n_sites, nz, nb, seqlen, skip, io_type):
     """K3/K4 against torch float64 autograd through the restated Euler unroll
     (tc_gan/networks/ssn.py:555-576, 619-633): outputs and gradients to rtol 1e-4 (BASELINE north_star).
