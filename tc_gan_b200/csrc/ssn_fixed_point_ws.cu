@@ -56,6 +56,12 @@
 #ifndef SSN_WS_PF
 #define SSN_WS_PF 2          // panel columns loaded this many columns ahead of use
 #endif
+#ifndef SSN_WS_RED
+#define SSN_WS_RED 0         // 0: 32-lane shuffle reduce-scatter of the 7 x 4 tile (default); 1: transpose through shared
+                             // memory -- half the instructions (67 against 124), measured 0.8 % SLOWER (74.16 against
+                             // 73.59 ms at configs[1]): the sweep is bound by the latency of its chain, not by issue slots
+#endif
+constexpr int WS_RED_PITCH = 36;                        // floats per output row of the transpose (32 lanes + skew)
 
 namespace ssn {
 
@@ -98,7 +104,7 @@ struct WsMisc {
 static_assert(sizeof(WsMisc) <= 512, "misc block");
 
 struct WsSmem {
-    int x_off, xe_off, tab_off, gtab_off, dv_off, ex_off, ref_off, misc_off, total;
+    int x_off, xe_off, tab_off, gtab_off, dv_off, ex_off, ref_off, red_off, misc_off, total;
 };
 template <class SH>
 __host__ __device__ inline WsSmem ws_smem_layout(int kpad, int n_sites, int tab_bytes) {
@@ -111,6 +117,7 @@ __host__ __device__ inline WsSmem ws_smem_layout(int kpad, int n_sites, int tab_
     L.dv_off = o;   o += 2 * SH::CW * 32 * 4;               // [half][contraction warp][lane] float
     L.ex_off = o;   o += 2 * SH::CW * 32 * 8;               // [half][contraction warp][lane] double
     L.ref_off = o;  o += 2 * 2 * SH::CW * 32 * 8;           // [half][r_ref, v_ref][contraction warp][lane] double
+    L.red_off = o;  o += SSN_WS_RED ? SH::CW * 4 * SH::TI * WS_RED_PITCH * 4 : 0;   // [contraction warp][4 TI outputs][pitch]
     L.misc_off = o; o += 512;
     L.total = o;
     return L;
@@ -419,6 +426,40 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
 #if SSN_WS_PROFILE
                     long long c3 = clock64(); tc[2] += c3 - c1;
 #endif
+#if SSN_WS_RED
+                    // ---- transpose through shared memory: every lane leaves its 4 TI partial sums in column `lane` of
+                    //      the warp's [4 TI][36] slab (conflict-free: bank = lane), then lane 4 * row + stimulus reads
+                    //      the 32 partials of its output as 8 LDS.128 (rows 36 floats apart: a quarter warp covers all
+                    //      32 banks) and adds them up.  28 STS + 8 LDS.128 + 31 FADD against 31 SHFL + 62 SEL + 31
+                    //      FADD of the shuffle version: the contraction warps are short of issue slots, not of LSU ----
+                    float out = 0.f;
+                    {
+                        float *red = reinterpret_cast<float *>(smem + L.red_off) + cwarp * (4 * TI * WS_RED_PITCH) + lane;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) {
+                                float lo, hi;
+                                unpack2(ap[q][b], lo, hi);
+                                red[(4 * (2 * q) + b) * WS_RED_PITCH] = lo;
+                                red[(4 * (2 * q + 1) + b) * WS_RED_PITCH] = hi;
+                            }
+                            if (ODD) red[(4 * (TI - 1) + b) * WS_RED_PITCH] = as[b];
+                        }
+                        __syncwarp();
+                        if (lane < 4 * TI) {
+                            const float4 *row = reinterpret_cast<const float4 *>(
+                                reinterpret_cast<const float *>(smem + L.red_off) + cwarp * (4 * TI * WS_RED_PITCH) + lane * WS_RED_PITCH);
+                            float4 v[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] = row[k];
+                            float s8[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) s8[k] = (v[k].x + v[k].y) + (v[k].z + v[k].w);
+                            out = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
+                        }
+                    }
+#else
                     // ---- 32-lane reduce-scatter: row over lane bits 4..2, stimulus over bits 1..0 ----
                     float out;
                     {
@@ -468,6 +509,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                             out = keep + __shfl_xor_sync(fullm, send, 1);
                         }
                     }
+#endif
                     // lane = 4 * row + stimulus: hand the sum to the update warp
                     dvbuf[(h * CW + cwarp) * 32 + lane] = out;
                     __syncwarp();

@@ -38,13 +38,26 @@ __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef SSN_MBAR_HINT_NS
+#define SSN_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned done = 0;
-    while (!done)
+    while (!done) {
+#if SSN_MBAR_HINT_NS > 0
+        // suspend-time hint: the warp may stay suspended this long before try_wait returns false (it is woken when the
+        // phase completes), so a waiting warp polls -- and takes issue slots from its scheduler -- less often
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;"
+            " selp.u32 %0, 1, 0, p; }"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"((unsigned)SSN_MBAR_HINT_NS) : "memory");
+#else
         asm volatile(
             "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;"
             " selp.u32 %0, 1, 0, p; }"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
+    }
 }
 __device__ __forceinline__ void st_async_v4(unsigned addr, float4 v, unsigned bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
