@@ -470,7 +470,7 @@ def run_secondary_only(args):
 
 def run_wgan(args):
     """Full WGAN-GP training steps (5 critic updates + 1 generator update per step) with the torch MLP
-    critic of tc_gan_b200.gan around the CUDA generator; synthetic 'true' tuning curves."""
+    critic of tc_gan_b200.gan around the CUDA generator; 'true' tuning curves sampled from the true-parameter SSN."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -482,8 +482,16 @@ def run_wgan(args):
         dist.init_process_group('nccl', device_id=dev)
     mode = 'fixed_point' if args.workload == 'wgan_fp' else 'bptt'
     num_models = 256 if mode == 'fixed_point' else 128
-    data = np.abs(np.random.RandomState(0).randn(1024, 8)).astype(np.float32) * 10
+    # 'true' tuning curves from the true-parameter SSN through the solver (as run/gan.py draws its data set), the
+    # generator starting from perturbed parameters (init_disturbance of run/gan.py:345-352)
+    from tc_gan_b200 import ssnode
+    jds = ssnode.new_JDS()
+    data, _ = ssnode.sample_tuning_curves(sample_sites=[0], NZ=512, seed=1, N=N_SITES, J=jds['J'], D=jds['D'], S=jds['S'])
+    data = np.asarray(data, dtype=np.float32)
+    if data.shape[0] == 8 and data.shape[1] != 8:
+        data = data.T
     g = gan.SSNWassersteinGAN(data, num_sites=N_SITES, mode=mode, num_models=num_models, sample_sites=(0,),
+                              J=jds['J'] * 0.9, D=jds['D'] * 0.9, S=jds['S'] * 0.95,
                               critic_iters_init=5, critic_iters=5, device=dev)
     steps = g.learning()
 
