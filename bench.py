@@ -303,6 +303,15 @@ def time_gan_step(workload, steps, warmup, dev, world, rank, peak):
         if flop.get(name):
             ent['tflops'] = flop[name] / (tot_ms / n * 1e-3) * 1e-12
             ent['fp32_roofline_frac'] = ent['tflops'] / peak
+        if name.startswith('ssn_euler_cluster_kernel') and flop.get(name):
+            # shared-memory view (north_star: 'fraction of the FP32/SMEM roofline'): per time step a CTA of the 4-CTA
+            # cluster issues, per warp and column step, 7 LDS.128 of W and 8 of the panel = 15 x 512 B, 7 column steps,
+            # 8 warps; peak 128 B per clock and SM
+            steps_done = seqlen if name.endswith('fwd') else seqlen - 1
+            smem_bytes = 15 * 512.0 * 7 * 8 * 4 * steps_done * nz
+            smem_peak = 148 * 128.0 * (peak / (148 * 128 * 2.0)) * 1e12          # B/s at the clock of the FP32 peak
+            ent['smem'] = {'achieved_gbs': smem_bytes / (tot_ms / n * 1e-3) * 1e-9, 'peak_gbs': smem_peak * 1e-9,
+                           'frac': smem_bytes / (tot_ms / n * 1e-3) / smem_peak}
         if name == 'ssn_bptt_param_grad_tc_kernel' and flop.get(name):
             # tensor-pipe view: three kind::tf32 MMAs per product (hi/lo split) on 128 x 208 tiles of the 402 x 402
             # output (512 x 416 computed); peak = half the measured dense bf16 rate (TF32 runs at half the bf16 rate;
