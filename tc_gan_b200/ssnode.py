@@ -363,8 +363,9 @@ def _start_gather(drawn, out, row0, num, host_threads):
         out = np.empty((num,) + first.shape, dtype=first.dtype)
     elif out.shape[1:] != first.shape or out.dtype != first.dtype:
         return None
-    # a quarter of the threads: the solver's own staging threads need the memory bandwidth more
-    return _Gather(zs, out, row0, max(1, (host_threads or 16) // 4))
+    # half of the threads: the solver's own staging threads run at the same time (measured at 1024 networks x 1.3 MB:
+    # 4 threads need 110 ms for float64 Z, longer than the 85 ms solve they are meant to hide under)
+    return _Gather(zs, out, row0, max(1, (host_threads or 16) // 2))
 
 
 def _generate_weight_from_z(Z, jds):
