@@ -432,7 +432,9 @@ def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
         finally:
             if gather is not None:
                 zs_out = gather.join()
-        ok = (errors == 0).all(axis=1) & np.isfinite(Rs).all(axis=(1, 2))
+        # a NaN or Inf anywhere in a network's rates survives the sum (rates are bounded by rate_hard_bound, no overflow):
+        # one pass over Rs instead of a boolean copy of it
+        ok = (errors == 0).all(axis=1) & np.isfinite(Rs.sum(axis=(1, 2)))
         for i in np.flatnonzero(~ok):
             err = errors[i].copy()
             err[(err == 0) & ~np.isfinite(Rs[i]).all(axis=1)] = 1          # ssnode.py:257-262
@@ -442,6 +444,7 @@ def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
             counter[sol.error] += 1
             if check:
                 raise sol.to_exception()
+        all_ok = bool(ok.all())
         if gather is not None:
             good = np.flatnonzero(ok)
             if len(good) < len(drawn):                     # close up the rows of the rejected networks
@@ -451,13 +454,14 @@ def find_fixed_points(num, Z_W_gen, exts, method='parallel', **common_kwargs):
             zs_rows += len(good)
         else:
             kept_z.extend(drawn[i][0] for i in np.flatnonzero(ok))
-        kept_R.append(Rs[ok])
-        kept_it.append(iters[ok])
+        kept_R.append(Rs if all_ok else Rs[ok])
+        kept_it.append(iters if all_ok else iters[ok])
 
     if zs_out is not None:
         if zs_rows == 0:
             raise ValueError('find_fixed_points: Z_W_gen was exhausted before any network converged')
-        xs, its = np.concatenate(kept_R), np.concatenate(kept_it)
+        xs = kept_R[0] if len(kept_R) == 1 else np.concatenate(kept_R)
+        its = kept_it[0] if len(kept_it) == 1 else np.concatenate(kept_it)
         Zs = zs_out if zs_rows == len(zs_out) else zs_out[:zs_rows].copy()
         return Zs, xs, FixedPointsInfo(_Solutions(xs, its), counter, sum(counter.values()), 0)
     if not kept_z:
