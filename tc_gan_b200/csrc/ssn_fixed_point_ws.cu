@@ -56,6 +56,9 @@
 #ifndef SSN_WS_PF
 #define SSN_WS_PF 2          // panel columns loaded this many columns ahead of use
 #endif
+#ifndef SSN_WS_DIAG
+#define SSN_WS_DIAG 0        // timing diagnostics (WRONG results): 1 no FMAs, 2 no reduce-scatter, 4 trivial f, 8 no remote publish of values
+#endif
 #ifndef SSN_WS_RED
 #define SSN_WS_RED 0         // 0: 32-lane shuffle reduce-scatter of the 7 x 4 tile (default); 1: transpose through shared
                              // memory -- half the instructions (67 against 124), measured 0.8 % SLOWER (74.16 against
@@ -358,9 +361,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                             const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                             for (int b = 0; b < 4; ++b) {
+#if SSN_WS_DIAG & 1
+                                as[b] += xv[b];
+#elif SSN_WS_DIAG & 16
+                                if (ODD) as[b] = fmaf(ws[c], xv[b], as[b]);       // 1/7 of the FMA work, sane magnitudes
+#else
 #pragma unroll
                                 for (int q = 0; q < NP; ++q) ffma2(ap[q][b], wp[q][c], xv[b]);
                                 if (ODD) as[b] = fmaf(ws[c], xv[b], as[b]);
+#endif
                             }
                         }
                     };
@@ -426,7 +435,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
 #if SSN_WS_PROFILE
                     long long c3 = clock64(); tc[2] += c3 - c1;
 #endif
-#if SSN_WS_RED
+#if SSN_WS_DIAG & 2
+                    float out = as[lane & 3];
+                    {
+                        float lo, hi;
+                        unpack2(ap[0][lane & 3], lo, hi);
+                        out += lo * 1e-30f;
+                    }
+#elif SSN_WS_RED
                     // ---- transpose through shared memory: every lane leaves its 4 TI partial sums in column `lane` of
                     //      the warp's [4 TI][36] slab (conflict-free: bank = lane), then lane 4 * row + stimulus reads
                     //      the 32 partials of its output as 8 LDS.128 (rows 36 floats apart: a quarter warp covers all
@@ -737,8 +753,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ssn_fp_ws_kernel(const RwArgs a
                         const bool lv = owner[g] && slot_live;
                         const double vv = ref_slot(h, 1, g) + (double)dv;
                         bool rare;
+#if SSN_WS_DIAG & 4
+                        rare = false;
+                        double fv = vv > 0.0 ? 0.5 * vv : 0.0;
+#else
                         double fv = io_eval_common(a, tab, vv, rare);
                         if (rare) fv = io_eval_exact(a, vv);                       // beyond the tables: diverging networks
+#endif
                         const double eps_own = grow[g] < N ? a.eps_E : a.eps_I;
                         const double d = lv ? (fv - sr[h][g]) * eps_own : 0.0;     // r_new - r_old
                         const double step = fabs(d);

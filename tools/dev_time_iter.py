@@ -24,5 +24,6 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 rounds = nz / rc.value
+print('  mean sweeps reported %.1f (lib %s)' % (float(it.float().mean()), os.environ.get('SSN_LIBNAME', 'libssnode')))
 print('dbg=%s cluster=%d resident=%d nz=%d: %.3f ms -> %.2f us/sweep = %.0f cycles @1.965GHz (incl. W load amortised over %d sweeps)' % (
     os.environ.get('SSN_DBG', '0'), cs.value, rc.value, nz, ms, ms * 1e3 / (rounds * maxit), ms * 1e3 / (rounds * maxit) * 1965, maxit))
