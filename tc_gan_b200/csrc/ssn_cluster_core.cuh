@@ -107,10 +107,9 @@ __device__ __forceinline__ void load_matrix_slice(float *Wsm, const float *__res
 // The accumulators are packed stimulus pairs (b, b+1): one fma.rn.f32x2 per pair with the broadcast W element, its
 // x operand being the register pair the panel's LDS.128 delivered -- half the issue slots of scalar FFMAs and no
 // register-bank conflicts (the scalar version measured 54 % of its FFMAs with a 2-cycle conflict).  Measured on the
-// BPTT step at configs[2] (SSN_CP build switch): 1 scalar FFMA + W rows of the next column step requested early
-// 53.2 ms, 0 scalar 52.5, 2 packed + early W 50.1, 3 packed 47.8 (default) -- the loop is bound by the 15 LDS.128
-// per 112 packed FMAs (60 wavefronts per warp and column step), not by issue slots, and the prefetch only costs
-// registers.
+// BPTT step at configs[2]: scalar FFMA + W rows of the next column step requested early 53.2 ms, scalar 52.5,
+// packed + early W 50.1, packed 47.8 (kept) -- the loop is bound by the 15 LDS.128 per 112 packed FMAs (60
+// wavefronts per warp and column step), not by issue slots, and the prefetch only costs registers.
 __device__ __forceinline__ unsigned long long bcast2(float x) {
     unsigned long long v;
     asm("mov.b64 %0, {%1, %1};" : "=l"(v) : "f"(x));
@@ -119,9 +118,6 @@ __device__ __forceinline__ unsigned long long bcast2(float x) {
 __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long a, unsigned long long b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
-#ifndef SSN_CP
-#define SSN_CP 3
-#endif
 template <int TI, int KL>
 __device__ __forceinline__ void contract_panel(float (&acc)[TI][TB], const float *Wsm, const float4 *X4,
                                                int P, int kpad, int buf, const int (&wrow)[TI], int kl) {
@@ -130,7 +126,6 @@ __device__ __forceinline__ void contract_panel(float (&acc)[TI][TB], const float
     const float4 *wp[TI];
 #pragma unroll
     for (int t = 0; t < TI; ++t) wp[t] = reinterpret_cast<const float4 *>(Wsm) + wrow[t] * kp4 + kl;
-#if SSN_CP >= 2
     unsigned long long a2[TI][TB / 2];
 #pragma unroll
     for (int t = 0; t < TI; ++t)
@@ -138,67 +133,31 @@ __device__ __forceinline__ void contract_panel(float (&acc)[TI][TB], const float
         for (int b = 0; b < TB / 2; ++b) a2[t][b] = 0ull;
     const ulonglong2 *Xa = reinterpret_cast<const ulonglong2 *>(X4 + (buf * 2 + 0) * P + 5 * kl);
     const ulonglong2 *Xb = Xa + P;
-#else
-#pragma unroll
-    for (int t = 0; t < TI; ++t)
-#pragma unroll
-        for (int b = 0; b < TB; ++b) acc[t][b] = 0.f;
-    const float4 *Xa = X4 + (buf * 2 + 0) * P + 5 * kl;
-    const float4 *Xb = Xa + P;
-#endif
-    float4 w[TI];
-#pragma unroll
-    for (int t = 0; t < TI; ++t) w[t] = wp[t][0];
 #pragma unroll 1
     for (int s = 0; s < nsteps; ++s) {
-#if SSN_CP == 1 || SSN_CP == 2
-        float4 wn[TI];
-        const int sn = s + 1 < nsteps ? s + 1 : s;
+        float4 w[TI];
 #pragma unroll
-        for (int t = 0; t < TI; ++t) wn[t] = wp[t][sn * KL];
-#else
-        if (s > 0) {
-#pragma unroll
-            for (int t = 0; t < TI; ++t) w[t] = wp[t][s * KL];
-        }
-#endif
+        for (int t = 0; t < TI; ++t) w[t] = wp[t][s * KL];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const auto xa = Xa[s * 5 * KL + q];
-            const auto xb = Xb[s * 5 * KL + q];
+            const ulonglong2 xa = Xa[s * 5 * KL + q];
+            const ulonglong2 xb = Xb[s * 5 * KL + q];
 #pragma unroll
             for (int t = 0; t < TI; ++t) {
                 const float wq = q == 0 ? w[t].x : q == 1 ? w[t].y : q == 2 ? w[t].z : w[t].w;
-#if SSN_CP >= 2
                 const unsigned long long ww = bcast2(wq);
                 fma2(a2[t][0], ww, xa.x);
                 fma2(a2[t][1], ww, xa.y);
                 fma2(a2[t][2], ww, xb.x);
                 fma2(a2[t][3], ww, xb.y);
-#else
-                acc[t][0] = fmaf(wq, xa.x, acc[t][0]);
-                acc[t][1] = fmaf(wq, xa.y, acc[t][1]);
-                acc[t][2] = fmaf(wq, xa.z, acc[t][2]);
-                acc[t][3] = fmaf(wq, xa.w, acc[t][3]);
-                acc[t][4] = fmaf(wq, xb.x, acc[t][4]);
-                acc[t][5] = fmaf(wq, xb.y, acc[t][5]);
-                acc[t][6] = fmaf(wq, xb.z, acc[t][6]);
-                acc[t][7] = fmaf(wq, xb.w, acc[t][7]);
-#endif
             }
         }
-#if SSN_CP == 1 || SSN_CP == 2
-#pragma unroll
-        for (int t = 0; t < TI; ++t) w[t] = wn[t];
-#endif
     }
-#if SSN_CP >= 2
 #pragma unroll
     for (int t = 0; t < TI; ++t)
 #pragma unroll
         for (int b = 0; b < TB / 2; ++b)
             asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[t][2 * b]), "=f"(acc[t][2 * b + 1]) : "l"(a2[t][b]));
-#endif
 }
 
 // ---- ownership after the reduce-scatter ------------------------------------------------
