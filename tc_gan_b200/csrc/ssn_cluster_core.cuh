@@ -75,7 +75,7 @@ __device__ __forceinline__ void load_matrix_slice(float *Wsm, const float *__res
     const int total = rows_here * kpad;
     if (!TRANSPOSED) {
         // consecutive threads walk along a row of W: coalesced global reads, conflict-free stores
-#pragma unroll 8
+#pragma unroll 16
         for (int idx = tid; idx < total; idx += nthreads) {
             const int r = idx / kpad, j = idx - r * kpad;
             const int i = row_base + r;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void load_matrix_slice(float *Wsm, const float *__res
     } else {
         // slice row r holds column (row_base + r) of W: Wsm[r][j] = W[j][row_base + r].
         // Consecutive threads take consecutive r, so global reads still run along a row of W.
-#pragma unroll 8
+#pragma unroll 16
         for (int idx = tid; idx < total; idx += nthreads) {
             const int j = idx / rows_here, r = idx - j * rows_here;
             float v = 0.f;

@@ -311,13 +311,33 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                         }
                         ++sweeps;
                         // classical Gram-Schmidt: h_i = <w, v_i> (i <= j), one cluster reduction ...
-                        for (int i = 0; i <= j; ++i) {
-                            float vi[TO], p = 0.f;
-                            load_vec(i, vi);
+                        // (the basis vectors v_0..v_j come from the L2 scratch: all loads of a step are issued together and
+                        // kept in registers for the orthogonalisation below -- one L2 latency per step instead of 2 (j + 1))
+                        constexpr bool CACHE = TO <= 4;
+                        float vb[CACHE ? GM : 1][TO];
+                        if constexpr (CACHE) {
 #pragma unroll
-                            for (int u = 0; u < TO; ++u) p = fmaf(wv[u], vi[u], p);
-                            p = stim_lane_sum<KL>(p);
-                            if (warp_writer) wp_mine[i] = p;
+                            for (int i = 0; i < GM; ++i)
+                                if (i <= j) load_vec(i, vb[i]);
+#pragma unroll
+                            for (int i = 0; i < GM; ++i)
+                                if (i <= j) {
+                                    float p = 0.f;
+#pragma unroll
+                                    for (int u = 0; u < TO; ++u) p = fmaf(wv[u], vb[i][u], p);
+                                    p = stim_lane_sum<KL>(p);
+                                    if (warp_writer) wp_mine[i] = p;
+                                }
+                        } else {
+#pragma unroll 4
+                            for (int i = 0; i <= j; ++i) {
+                                float vi[TO], p = 0.f;
+                                load_vec(i, vi);
+#pragma unroll
+                                for (int u = 0; u < TO; ++u) p = fmaf(wv[u], vi[u], p);
+                                p = stim_lane_sum<KL>(p);
+                                if (warp_writer) wp_mine[i] = p;
+                            }
                         }
                         cluster_sum(j + 1, fin);
                         // ... w' = w - sum h_i v_i, and a second (one value) reduction for |w'|^2.  Taking the norm from
@@ -329,15 +349,28 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                         float vnext[TO], hsq = 0.f;
 #pragma unroll
                         for (int u = 0; u < TO; ++u) vnext[u] = wv[u];
-                        if (!frozen)
-                            for (int i = 0; i <= j; ++i) {
-                                float vi[TO];
-                                load_vec(i, vi);
-                                const float h = fin_mine[i];
-                                hsq = fmaf(h, h, hsq);
+                        if (!frozen) {
+                            if constexpr (CACHE) {
 #pragma unroll
-                                for (int u = 0; u < TO; ++u) vnext[u] = fmaf(-h, vi[u], vnext[u]);
+                                for (int i = 0; i < GM; ++i)
+                                    if (i <= j) {
+                                        const float h = fin_mine[i];
+                                        hsq = fmaf(h, h, hsq);
+#pragma unroll
+                                        for (int u = 0; u < TO; ++u) vnext[u] = fmaf(-h, vb[i][u], vnext[u]);
+                                    }
+                            } else {
+#pragma unroll 4
+                                for (int i = 0; i <= j; ++i) {
+                                    float vi[TO];
+                                    load_vec(i, vi);
+                                    const float h = fin_mine[i];
+                                    hsq = fmaf(h, h, hsq);
+#pragma unroll
+                                    for (int u = 0; u < TO; ++u) vnext[u] = fmaf(-h, vi[u], vnext[u]);
+                                }
                             }
+                        }
                         {
                             float p = 0.f;
 #pragma unroll
@@ -591,7 +624,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                         const int ab = ah * 2 + bh;
                         const float cJ = a.wc.sJ[ab], cD = a.wc.sD[ab];
                         const float *gt = gtab + ab * N;
-#pragma unroll 2
+#pragma unroll 8
                         for (int idx = tid; idx < nj * N; idx += nthreads) {
                             const int ii = idx / nj, jl = idx - ii * nj;
                             const int i = ah * N + ii, j = j_lo + jl;
