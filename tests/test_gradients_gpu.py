@@ -222,6 +222,34 @@ def test_euler_long_unroll_reaches_fixed_point(ops, oracle):
     np.testing.assert_allclose(avg.cpu().numpy(), R.cpu().numpy(), rtol=5e-4, atol=5e-4)
 
 
+def test_bptt_of_a_long_unroll_equals_the_implicit_gradient(ops, oracle):
+    """Cross-check of the two gradient paths at BASELINE size (2N=402, 8 stimuli): the gradient of a loss on the final
+    state of a LONG Euler unroll (K3 + K4 + K4b: 2000 steps with the fixed-point solver's dt / tau, by which the
+    dynamics has converged) equals the implicit-function-theorem gradient at the fixed point (K1 + K2: GMRES on the
+    adjoint system).  Two different algorithms, five kernels, no oracle in between: dL/d(J, D, S) to 2e-4."""
+    import torch
+    n_sites, nz = 201, 3
+    jds = oracle.new_JDS()
+    exts = oracle.stimulus_input(oracle.DEFAULT_BANDWIDTHS, n_sites)
+    rs = np.random.RandomState(77)
+    z = tens(rs.rand(nz, 2 * n_sites, 2 * n_sites))
+    G = tens(rs.randn(nz, len(exts), 2 * n_sites))
+    grads = []
+    for path in ('bptt', 'ift'):
+        J, D, S = (tens(jds[k], torch.float64, grad=True) for k in 'JDS')
+        if path == 'bptt':
+            R, _, _ = ops.euler_ssn(z, J, D, S, tens(exts), seqlen=2000, skip_steps=1999, dt=0.0008,
+                                    tau_E=0.01589, tau_I=0.002)
+        else:
+            R, status, _ = ops.ssn_fixed_point(z, J, D, S, tens(exts), solver=ops.make_solver(atol=1e-9))
+            assert (status == 0).all()
+        (R * G).sum().backward()
+        grads.append([p.grad.cpu().numpy() for p in (J, D, S)] + [R.detach().cpu().numpy()])
+    np.testing.assert_allclose(grads[0][3], grads[1][3], rtol=1e-5, atol=1e-5)        # the states agree
+    for a, b in zip(grads[0][:3], grads[1][:3]):
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-4 * np.abs(b).max())
+
+
 def test_heterogeneous_input_gradients(ops, oracle):
     """heteroin / deg-heteroin generators (networks/ssn.py:645-727): stimulus scaled per
     neuron by 1 + V z_in; dL/dV through both gradient paths against float64 (torch autograd for BPTT,
