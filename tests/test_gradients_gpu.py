@@ -353,3 +353,17 @@ def test_no_grad_forward_stores_no_trajectory(ops, monkeypatch):
     avg2, _, _ = ops.euler_ssn(z, J, D, S, ext, seqlen=20, skip_steps=10)
     assert seen == [False, True] and not avg.requires_grad and avg2.requires_grad
     torch.testing.assert_close(avg, avg2.detach())
+
+
+@pytest.mark.parametrize('seed', [21, 22])
+def test_randomised_gradient_stress(ops, seed):
+    """24 random cases per seed of tools/dev_stress_grad.py: K2 (GMRES) and K3/K4/K4b against the float64 oracle
+    over sizes from 2N = 2 to 560 (every cluster width), ragged stimulus counts, all transfer functions, unrolls of
+    1..41 steps, to rtol 1e-4.  (460 cases of it ran clean on a B200 after the round-2 kernel changes.)"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CASES='24', SEED=str(seed))
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'dev_stress_grad.py')], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'done: 24 cases, 0 mismatches' in out.stdout, out.stdout[-3000:]
