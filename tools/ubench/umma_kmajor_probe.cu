@@ -78,7 +78,7 @@ __global__ void probe(const float *A, const float *B, float *D, long long *cycle
                      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                      : "r"(tb + ((unsigned)((warp % 4) * 32) << 16)) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (r == reps - 1 && tid < M)
+        if (r == reps - 1)
             for (int c = 0; c < N; ++c) D[tid * N + c] = __uint_as_float(v[c]);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -89,7 +89,7 @@ __global__ void probe(const float *A, const float *B, float *D, long long *cycle
 }
 template <int M>
 void run(const char *name) {
-    static float hA[M * KT], hB[N * KT], hD[M * N];
+    static float hA[M * KT], hB[N * KT], hD[128 * N];
     static double ref[M * N];
     srand(1);
     // tf32-exact inputs: small integers / 8
@@ -101,16 +101,28 @@ void run(const char *name) {
     cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, sizeof(hB), cudaMemcpyHostToDevice);
     const int smem = M * KT * 4 + N * KT * 4;
     cudaFuncSetAttribute(probe<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    for (int swap = 0; swap < 2; ++swap)
+    // (LBO = distance of the core matrices along K, SBO = along M/N: the swapped reading faults)
+    for (int swap = 0; swap < 1; ++swap)
         for (int terms = 1; terms <= 3; terms += 2) {
             cudaMemset(dD, 0xff, sizeof(hD));
             probe<M><<<1, 128, smem>>>(dA, dB, dD, dc, swap, 21, terms);
             cudaError_t e = cudaDeviceSynchronize();
             cudaMemcpy(hD, dD, sizeof(hD), cudaMemcpyDeviceToHost); cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
             double err = 0; int bad = 0;
-            for (int i = 0; i < M * N; ++i) { double d = fabs(hD[i] - terms * ref[i]); if (d > err) err = d; if (d > 1e-3) ++bad; }
-            printf("%s swap=%d terms=%d: %s, max abs err %g, bad %d of %d, %lld cycles per step (%d MMAs + commit + wait + tcgen05.ld + sync)\n",
-                   name, swap, terms, cudaGetErrorString(e), err, bad, M * N, hc, terms * KT / 8);
+            // which TMEM lane holds row m (M = 64 uses a different lane map than M = 128)
+            int lane_of[M];
+            for (int m = 0; m < M; ++m) {
+                lane_of[m] = -1;
+                for (int l = 0; l < 128 && lane_of[m] < 0; ++l) {
+                    bool ok = true;
+                    for (int c = 0; c < N; ++c) ok = ok && fabs(hD[l * N + c] - terms * ref[m * N + c]) < 1e-3;
+                    if (ok) lane_of[m] = l;
+                }
+                if (lane_of[m] < 0) ++bad; else { double d = 0; for (int c = 0; c < N; ++c) d = fmax(d, fabs(hD[lane_of[m] * N + c] - terms * ref[m * N + c])); if (d > err) err = d; }
+            }
+            if (terms == 1) { printf("%s: TMEM lane of rows 0, 1, 16, 17, 32, 63: %d %d %d %d %d %d\n", name, lane_of[0], lane_of[1], lane_of[16 % M], lane_of[17 % M], lane_of[32 % M], lane_of[63 % M]); }
+            printf("%s swap=%d terms=%d: %s, max abs err %g, rows not found %d of %d, %lld cycles per step (%d MMAs + commit + wait + tcgen05.ld + sync)\n",
+                   name, swap, terms, cudaGetErrorString(e), err, bad, M, hc, terms * KT / 8);
             if (e != cudaSuccess) exit(1);
         }
 }
