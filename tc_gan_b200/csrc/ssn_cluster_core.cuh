@@ -271,9 +271,14 @@ __device__ __forceinline__ float io_eval_fast(const IoConst<float> &c, float v) 
 // (|frac(n) log2 v| < 2 for n = 2.2, v < 1000) and the relative error is ~2e-7 instead of ~1e-6 for 2^(n log2 v);
 // no division, no branches.  (powf: 1 ulp, but ~60 instructions with slow paths, once per neuron, stimulus and step.)
 __device__ __forceinline__ void io_power_fast(const IoConst<float> &c, float v, float &f, float &df) {
-    const float p = exp2f(c.n_frac * __log2f(v));
-    float vm = 1.f;                                   // v^(n_int - 1)
-    for (int i = 1; i < c.n_int; ++i) vm *= v;
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(c.n_frac * __log2f(v)));
+    // v^(n_int - 1) from the bits of the exponent (n_int <= 8): straight-line code, no loop
+    const int e = c.n_int - 1;
+    const float v2 = v * v, v4 = v2 * v2;
+    float vm = (e & 1) ? v : 1.f;
+    vm = (e & 2) ? vm * v2 : vm;
+    vm = (e & 4) ? vm * v4 : vm;
     if (c.n_int >= 1) {
         df = c.nk * vm * p;
         f = c.k * (vm * v) * p;

@@ -194,11 +194,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
 #pragma unroll
                     for (int u = 0; u < TO; ++u) {
                         const float vt = v[u] + ext_own[u];
-                        float fv = 0.f, gv = 0.f;
-                        if (vt > 0.f) {
-                            if (pure_power || vt <= a.io.v0) io_power_fast(a.io, vt, fv, gv);
-                            else { fv = io_eval<float>(a.io, vt); gv = io_gain<float>(a.io, vt); }    // saturating branch
-                        }
+                        // power-law branch without a branch (the common case); the saturating branch of asym_tanh /
+                        // asym_linear only for the lanes above v0
+                        float fv, gv;
+                        io_power_fast(a.io, fmaxf(vt, 1e-30f), fv, gv);
+                        fv = vt > 0.f ? fv : 0.f;
+                        gv = vt > 0.f ? gv : 0.f;
+                        if (!pure_power && vt > a.io.v0) { fv = io_eval<float>(a.io, vt); gv = io_gain<float>(a.io, vt); }
                         const double r_old = state[u];
                         const double r_new = r_old + ((double)fv - r_old) * eps_own[u];
                         state[u] = r_new;
