@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
     const int T = seqlen - skip;
     double pen_dyn = 0.0, pen_rate = 0.0;
     unsigned phase = 0u;                                        // bit b: parity of the next completion of bars[b]
-    // publish one value per owned row into buffer nb of every CTA, then wait for the whole panel of that buffer
-    auto exchange = [&](const float (&val)[TO], const unsigned (&xo)[TO], int nb) {
+    // publish one value per owned row into buffer nb of every CTA ...
+    auto publish = [&](const float (&val)[TO], const unsigned (&xo)[TO], int nb) {
         const unsigned boff = nb ? buf_bytes : 0u;
 #pragma unroll
         for (int u = 0; u < TO; ++u)
@@ -123,12 +123,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                 for (int p = 0; p < MAX_CLUSTER; ++p)
                     if (p < csize) st_async_u32(xpeer[p] + xo[u] + boff, __float_as_uint(val[u]), bpeer[p] + 8u * nb);
             }
-        const unsigned bar = smem_u32(&bars[nb]);
-        if (tid == 0) mbar_arrive_expect_tx(bar, step_bytes);
-        mbar_wait(bar, (phase >> nb) & 1u);
+        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&bars[nb]), step_bytes);
+    };
+    // ... and wait for the whole panel of that buffer (after whatever work does not feed the peers)
+    auto await = [&](int nb) {
+        mbar_wait(smem_u32(&bars[nb]), (phase >> nb) & 1u);
         phase ^= 1u << nb;
     };
-
     for (;;) {
         if (rank == 0 && tid == 0) {
             const int n = atomicAdd(a.work_counter, 1);
@@ -181,9 +182,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                 }
                 cluster.sync();
                 int buf = 0;
-                float eps_f[TO];
+                float eps_f[TO], rstate[TO];
 #pragma unroll
-                for (int u = 0; u < TO; ++u) eps_f[u] = (float)eps_own[u];
+                for (int u = 0; u < TO; ++u) { eps_f[u] = (float)eps_own[u]; rstate[u] = 0.f; }
                 const bool pure_power = a.io.io_type == SSN_IO_POWER;
                 for (int t = 0; t < seqlen; ++t) {
                     float acc[TI][TB], v[TO], rpub[TO];
@@ -191,32 +192,36 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                     reduce_scatter<TI, KL>(acc, v, kl);
                     const int nbuf = buf ^ 1;
                     const bool keep = t >= skip;
+                    float r_prev[TO], gv[TO];
 #pragma unroll
                     for (int u = 0; u < TO; ++u) {
                         const float vt = v[u] + ext_own[u];
                         // power-law branch without a branch (the common case); the saturating branch of asym_tanh /
                         // asym_linear only for the lanes above v0
-                        float fv, gv;
-                        io_power_fast(a.io, fmaxf(vt, 1e-30f), fv, gv);
+                        float fv;
+                        io_power_fast(a.io, fmaxf(vt, 1e-30f), fv, gv[u]);
                         fv = vt > 0.f ? fv : 0.f;
-                        gv = vt > 0.f ? gv : 0.f;
-                        if (!pure_power && vt > a.io.v0) { fv = io_eval<float>(a.io, vt); gv = io_gain<float>(a.io, vt); }
-                        const double r_old = state[u];
-                        const double r_new = r_old + ((double)fv - r_old) * eps_own[u];
-                        state[u] = r_new;
-                        rpub[u] = (float)r_new;
+                        gv[u] = vt > 0.f ? gv[u] : 0.f;
+                        if (!pure_power && vt > a.io.v0) { fv = io_eval<float>(a.io, vt); gv[u] = io_gain<float>(a.io, vt); }
+                        r_prev[u] = rstate[u];
+                        rstate[u] = fmaf(eps_f[u], fv - rstate[u], rstate[u]);      // float32 state, as the reference (floatX)
+                        rpub[u] = rstate[u];
+                    }
+                    publish(rpub, xoff, nbuf);          // the peers wait for this: outputs to HBM and the penalties come after
+#pragma unroll
+                    for (int u = 0; u < TO; ++u)
                         if (valid[u] && active) {
                             if (keep) {
+                                const double r_new = (double)rpub[u];
                                 avg[u] += r_new;
                                 pen_rate += fmax(r_new - (double)a.threshold, 0.0);
-                                if (t > skip) pen_dyn += (r_new - r_old) * (r_new - r_old);
+                                if (t > skip) pen_dyn += (r_new - (double)r_prev[u]) * (r_new - (double)r_prev[u]);
                             }
                             const size_t o = net_base + (size_t)t * tslice + toff[u];
                             if (a.traj) a.traj[o] = rpub[u];
-                            if (a.gain) a.gain[o] = eps_f[u] * gv;
+                            if (a.gain) a.gain[o] = eps_f[u] * gv[u];
                         }
-                    }
-                    exchange(rpub, xoff, nbuf);
+                    await(nbuf);
                     buf = nbuf;
                 }
 #pragma unroll
@@ -278,17 +283,21 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                             if (active) {
                                 q = gain_k[u] * (float)lam;
                                 gext[u] += q;                             // dL/d ext = sum_k q_k, q_0 included
-                                if (tp > 0) a.adj[net_base + (size_t)(tp - 1) * tslice + toff[u]] = q;
-                                else q = 0.f;                             // q_0 pairs with r_0 = 0: nothing to publish
+                                if (tp == 0) q = 0.f;                     // q_0 pairs with r_0 = 0: nothing to publish
                             }
-                            if (active && tp == seqlen - 1)
-                                a.adj[net_base + (size_t)tp * tslice + toff[u]] = 0.f;   // q_seqlen = 0
                             r_next[u] = r_cur[u];
                             r_cur[u] = r_prev;
                             qpub[u] = q;
                         }
                     }
-                    exchange(qpub, xoff, nbuf);
+                    publish(qpub, xoff, nbuf);          // the peers wait for this: the stores to HBM come after
+#pragma unroll
+                    for (int u = 0; u < TO; ++u)
+                        if (valid[u] && active) {
+                            if (tp > 0) a.adj[net_base + (size_t)(tp - 1) * tslice + toff[u]] = qpub[u];
+                            if (tp == seqlen - 1) a.adj[net_base + (size_t)tp * tslice + toff[u]] = 0.f;   // q_seqlen = 0
+                        }
+                    await(nbuf);
                     buf = nbuf;
                 }
                 if (a.grad_ext) {
