@@ -150,12 +150,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
             const int stim_g = b0 + my_stim;
 
             unsigned xoff[TO];
-            double eps_own[TO], state[TO];             // r_k (forward) or lambda_{k+1} (backward)
+            double eps_own[TO];
             size_t goff[TO];                           // offset of (stim, row) inside one [nb][2N] slice
             size_t toff[TO];                           // ... inside one [nb][pitch] time slice of traj / gain / adj
 #pragma unroll
             for (int u = 0; u < TO; ++u) {
-                xoff[u] = 0u; eps_own[u] = 0.0; state[u] = 0.0; goff[u] = 0; toff[u] = 0;
+                xoff[u] = 0u; eps_own[u] = 0.0; goff[u] = 0; toff[u] = 0;
                 if (valid[u]) {
                     const int gr = row_base + own0 + u;
                     xoff[u] = 4u * (unsigned)panel_index(P, 0, gr, my_stim);
@@ -231,10 +231,12 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                 // ---- adjoint recursion, k = seqlen .. 1 (array index tp = k - 1) ----
                 const double w_dyn = a.w_dev ? a.w_dyn * (double)__ldg(a.w_dev) : a.w_dyn;
                 const double w_rate = a.w_dev ? a.w_rate * (double)__ldg(a.w_dev + 1) : a.w_rate;
-                float gavg[TO], r_cur[TO], r_next[TO], gext[TO];
+                const float w_rate_f = (float)w_rate, w_dyn2_f = (float)(2.0 * w_dyn);
+                float gavg[TO], r_cur[TO], r_next[TO], gext[TO], lstate[TO], omeps_f[TO];
 #pragma unroll
                 for (int u = 0; u < TO; ++u) {
-                    gavg[u] = 0.f; r_cur[u] = 0.f; r_next[u] = 0.f; gext[u] = 0.f;
+                    gavg[u] = 0.f; r_cur[u] = 0.f; r_next[u] = 0.f; gext[u] = 0.f; lstate[u] = 0.f;
+                    omeps_f[u] = (float)(1.0 - eps_own[u]);
                     if (valid[u] && active) {
                         gavg[u] = __ldg(a.g_avg + (size_t)net * slice + goff[u]) / (float)T;
                         r_cur[u] = __ldg(a.traj_in + net_base + (size_t)(seqlen - 1) * tslice + toff[u]);
@@ -266,22 +268,25 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_euler_cluster_kernel(const
                         qpub[u] = 0.f;
                         if (valid[u]) {
                             const float r_prev = r_prevs[u];
-                            double lam = 0.0;
+                            float lam = 0.f;
                             if (active) {
-                                double d = 0.0;
+                                float d = 0.f;
                                 if (k >= skip + 1) {
-                                    d = (double)gavg[u];
-                                    if (r_cur[u] > a.threshold) d += w_rate;
-                                    if (k >= skip + 2) d += 2.0 * w_dyn * ((double)r_cur[u] - (double)r_prev);
-                                    if (k <= seqlen - 1) d -= 2.0 * w_dyn * ((double)r_next[u] - (double)r_cur[u]);
+                                    d = gavg[u];
+                                    if (r_cur[u] > a.threshold) d += w_rate_f;
+                                    // d/dr_k of sum (r_{t+1} - r_t)^2: the two differences first, then one scaling
+                                    float dd = 0.f;
+                                    if (k >= skip + 2) dd = r_cur[u] - r_prev;
+                                    if (k <= seqlen - 1) dd -= r_next[u] - r_cur[u];
+                                    d = fmaf(w_dyn2_f, dd, d);
                                 }
-                                lam = d + (1.0 - eps_own[u]) * state[u] + (double)y[u];
+                                lam = fmaf(omeps_f[u], lstate[u], d) + y[u];
                             }
-                            state[u] = lam;                           // lambda_k
+                            lstate[u] = lam;                          // lambda_k (float32, like the reference's floatX graph)
                             // q_{k-1} = gain[k-1] * lambda_k, paired with r_{k-1} = traj[tp-1]
                             float q = 0.f;
                             if (active) {
-                                q = gain_k[u] * (float)lam;
+                                q = gain_k[u] * lam;
                                 gext[u] += q;                             // dL/d ext = sum_k q_k, q_0 included
                                 if (tp == 0) q = 0.f;                     // q_0 pairs with r_0 = 0: nothing to publish
                             }
