@@ -150,6 +150,22 @@ __device__ __forceinline__ double io_eval_common(const Args &a, const double *ta
     const bool above = v > a.io.v0;
     const bool upper = above && a.tab2_nodes > 0;                       // saturating branch of asym_tanh
     const double inv_h = upper ? (double)TAB2_PER_UNIT : (double)TAB_PER_UNIT;
+#ifndef SSN_WS_FEVAL
+#define SSN_WS_FEVAL 0
+#endif
+#if SSN_WS_FEVAL == 1
+    // Experiment (not the default): node index from FP32 arithmetic + F2I / I2D conversions, s in two dependent FP64
+    // operations instead of five, Estrin form.  Measured 2.8 % SLOWER at configs[1] (75.64 against 73.59 ms): the
+    // conversion instructions cost more than the three FP64 operations they replace (the 2^52 trick below has none);
+    // Estrin alone (SSN_WS_FEVAL=2) changes nothing (73.78 against 73.71 ms).
+    int i = __float2int_rn((vf - (upper ? a.iof.v0 : (float)TAB_V_MIN)) * (upper ? (float)TAB2_PER_UNIT : (float)TAB_PER_UNIT));
+    i = max(0, min(i, (upper ? a.tab2_nodes : a.tab_nodes) - 1));
+    const double *c = tab + TAB_COEF * (i + (upper ? a.tab_nodes : 0));
+    const double2 c01 = *reinterpret_cast<const double2 *>(c);
+    const double2 c23 = *reinterpret_cast<const double2 *>(c + 2);
+    const double s = fma(v - (upper ? a.io.v0 : TAB_V_MIN), inv_h, -(double)i);
+    double f = fma(s * s, fma(s, c23.y, c23.x), fma(s, c01.y, c01.x));
+#else
     const double x = (v - (upper ? a.io.v0 : TAB_V_MIN)) * inv_h;
     // round to nearest by adding 1.5 * 2^52: the integer lands in the low word, the rounded value comes back by subtraction
     const double xm = x + 6755399441055744.0;
@@ -159,7 +175,12 @@ __device__ __forceinline__ double io_eval_common(const Args &a, const double *ta
     const double *c = tab + TAB_COEF * (i + (upper ? a.tab_nodes : 0));
     const double2 c01 = *reinterpret_cast<const double2 *>(c);
     const double2 c23 = *reinterpret_cast<const double2 *>(c + 2);
+#if SSN_WS_FEVAL == 2
+    double f = fma(s * s, fma(s, c23.y, c23.x), fma(s, c01.y, c01.x));      // Estrin: depth 2
+#else
     double f = fma(s, fma(s, fma(s, c23.y, c23.x), c01.y), c01.x);
+#endif
+#endif
     const float flow = a.iof.k * exp2f(a.iof.n * __log2f(fmaxf(vf, 1e-30f)));
     f = vf < (float)TAB_V_MIN ? (double)flow : f;
     f = v > 0.0 ? f : (v != v ? v : 0.0);
