@@ -8,7 +8,8 @@
 // with Phi = diag f'(W r + I) and g = dL/dr.  The adjoint system is solved by restarted GMRES(16) on the
 // cluster-resident machinery of K1 (here the cluster holds W^T in shared memory): one Arnoldi step is one
 // skinny contraction W^T (Phi v) of the 8-stimulus panel -- the eight systems of a network share W^T, differ in
-// Phi and run in lockstep -- plus two cluster-wide reductions (Gram-Schmidt coefficients; norm of the new vector).  The
+// Phi and run in lockstep -- plus two cluster-wide reductions (Gram-Schmidt coefficients; norm of the new vector, whose
+// barrier also carries the publish of the next direction).  The
 // Krylov basis lives in an L2-resident scratch (16 vectors x 16 KB per resident cluster), the small least-squares problem
 // is updated with Givens rotations per stimulus, and every cycle starts from the TRUE residual g - A mu, which
 // is also the stopping test: ||g - A mu||_2 <= rtol ||g||_2.  A solve on which two consecutive cycles make no
@@ -299,6 +300,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                     }
 #pragma unroll
                     for (int i = 0; i < GM; ++i) { cs[i] = 1.f; sn[i] = 0.f; }
+                    // The panel holds Phi u_j with u_j = v_j / scale: the new direction is published BEFORE its norm is
+                    // known (the publish shares the cluster barrier of the norm's reduction) and the contraction's
+                    // result is scaled afterwards -- two cluster barriers per Arnoldi step instead of three.
+                    float scale = 1.f;
                     cluster.sync();
                     for (int j = 0; j < GM && ctl[1] != 0xffu; ++j) {
                         float wv[TO];
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                             contract_panel<TI, KL>(acc, Wsm, X4, P, kpad, 0, wrow, kl);
                             reduce_scatter<TI, KL>(acc, y, kl);
 #pragma unroll
-                            for (int u = 0; u < TO; ++u) wv[u] = valid[u] ? vcur[u] - y[u] : 0.f;   // w = A v_j
+                            for (int u = 0; u < TO; ++u) wv[u] = valid[u] ? fmaf(-scale, y[u], vcur[u]) : 0.f;   // w = A v_j
                         }
                         ++sweeps;
                         // classical Gram-Schmidt: h_i = <w, v_i> (i <= j), one cluster reduction ...
@@ -378,6 +383,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                             p = stim_lane_sum<KL>(p);
                             if (warp_writer) wp_mine[0] = p;
                         }
+                        publish(vnext);                 // unnormalised; every CTA is past its contraction (barrier above)
                         cluster_sum(1, fin2);
                         if (!frozen) {
                             // new column of the Hessenberg matrix, rotated into R (every thread of the stimulus
@@ -415,23 +421,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) ssn_ift_cluster_kernel(const I
                             kd = j + 1;
                             if (brk || fabsf(gnext) <= 0.7f * tolabs || j == GM - 1) {
                                 frozen = true;
+                                scale = 0.f;
                                 if (cta_writer) atomicOr(&ctl[1], 1u << my_stim);
 #pragma unroll
                                 for (int u = 0; u < TO; ++u) vnext[u] = 0.f;
                             } else {
-                                const float inv = 1.f / hn;
+                                scale = 1.f / hn;
 #pragma unroll
-                                for (int u = 0; u < TO; ++u) vnext[u] *= inv;
+                                for (int u = 0; u < TO; ++u) vnext[u] *= scale;
                             }
                         } else {
+                            scale = 0.f;
 #pragma unroll
                             for (int u = 0; u < TO; ++u) vnext[u] = 0.f;
                         }
 #pragma unroll
                         for (int u = 0; u < TO; ++u) vcur[u] = vnext[u];
                         if (j + 1 < GM) store_vec(j + 1, vcur);
-                        publish(vcur);
-                        cluster.sync();
+                        __syncthreads();                // ctl[1], R and the rotated right-hand side of this step
                         if (ctl[1] == 0xffu) break;
                     }
                     // ---------- mu += V y,  R y = gamma ----------
